@@ -1,0 +1,212 @@
+// api.cu -- the C ABI of libggml_b200.so (include/ggml_b200.h): argument validation, error plumbing and
+// per-device caches.  No torch types, no allocation, no synchronisation: every entry point validates on
+// the host, enqueues on the caller's stream and returns a status code.
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+
+#include "ggb_common.cuh"
+
+// kernels (one translation unit each)
+int ggb_dequantize_impl(const void *W, int type, int64_t nelem, void *out, int out_dtype, cudaStream_t stream);
+int ggb_quantize_q8_1_impl(const void *X, int x_dtype, int64_t rows, int64_t K, void *out, int layout, int wtype,
+                           cudaStream_t stream);
+int ggb_mmvq_impl(const void *W, const void *X, void *Y, int type, int xy_dtype, int64_t B, int64_t K, int64_t N,
+                  void *ws, int64_t ws_bytes, cudaStream_t stream);
+int64_t ggb_mmvq_workspace_bytes_impl(int type, int64_t B, int64_t K, int64_t N);
+int ggb_mmq_impl(const void *W, const void *X, void *Y, int type, int xy_dtype, int64_t M, int64_t K, int64_t N,
+                 int64_t ldy, void *ws, int64_t ws_bytes, cudaStream_t stream);
+int64_t ggb_mmq_workspace_bytes_impl(int type, int64_t M, int64_t K, int64_t N);
+
+// ---------------------------------------------------------------- errors
+static thread_local char g_err[512] = "";
+
+void ggb_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+// ---------------------------------------------------------------- per-device cache
+const DeviceInfo &ggb_device_info() {
+    static DeviceInfo info[64];
+    static std::once_flag once[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    std::call_once(once[dev], [dev]() {
+        int v = 0;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        info[dev].sm_count = v > 0 ? v : 148;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        info[dev].max_smem_optin = v > 0 ? v : 232448;
+    });
+    return info[dev];
+}
+
+// ---------------------------------------------------------------- type table
+static int block_elems(int type) {
+    switch (type) {
+        case T_Q4_0: case T_Q4_1: case T_Q5_0: case T_Q5_1: case T_Q8_0: return 32;
+        case T_Q2_K: case T_Q3_K: case T_Q4_K: case T_Q5_K: case T_Q6_K: return 256;
+        default: return 0;
+    }
+}
+static int block_bytes(int type) {
+    switch (type) {
+        case T_Q4_0: return 18;  case T_Q4_1: return 20;  case T_Q5_0: return 22;
+        case T_Q5_1: return 24;  case T_Q8_0: return 34;
+        case T_Q2_K: return 84;  case T_Q3_K: return 110; case T_Q4_K: return 144;
+        case T_Q5_K: return 176; case T_Q6_K: return 210;
+        default: return 0;
+    }
+}
+
+static bool check_type(const char *fn, int type) {
+    if (block_elems(type) == 0) {
+        ggb_set_error("%s: unsupported ggml type %d", fn, type);
+        return false;
+    }
+    return true;
+}
+static bool check_dtype(const char *fn, int dt) {
+    if (dt != GGB_F32 && dt != GGB_F16 && dt != GGB_BF16) {
+        ggb_set_error("%s: unknown dtype code %d", fn, dt);
+        return false;
+    }
+    return true;
+}
+
+extern "C" {
+
+int ggb_version(void) { return GGB_VERSION; }
+const char *ggb_last_error(void) { return g_err; }
+int ggb_block_elems(int type) { return block_elems(type); }
+int ggb_block_bytes(int type) { return block_bytes(type); }
+
+int ggb_dequantize(const void *W, int type, int64_t m, int64_t n, void *out, int out_dtype, void *stream) {
+    g_err[0] = 0;
+    if (!check_type("ggb_dequantize", type)) return GGB_E_TYPE;
+    if (!check_dtype("ggb_dequantize", out_dtype)) return GGB_E_DTYPE;
+    if (m < 0 || n < 0 || n % block_elems(type) != 0) {
+        ggb_set_error("ggb_dequantize: shape [%lld, %lld] is not a whole number of %d-value blocks per row",
+                      (long long)m, (long long)n, block_elems(type));
+        return GGB_E_SHAPE;
+    }
+    if (m == 0 || n == 0) return GGB_OK;
+    if (!W || !out) {
+        ggb_set_error("ggb_dequantize: null pointer");
+        return GGB_E_ARG;
+    }
+    if (reinterpret_cast<uintptr_t>(out) & 15) {
+        ggb_set_error("ggb_dequantize: out must be 16-byte aligned");
+        return GGB_E_ARG;
+    }
+    if (reinterpret_cast<uintptr_t>(W) & 1) {
+        ggb_set_error("ggb_dequantize: W must be 2-byte aligned");
+        return GGB_E_ARG;
+    }
+    return ggb_dequantize_impl(W, type, m * n, out, out_dtype, static_cast<cudaStream_t>(stream));
+}
+
+int64_t ggb_q8_1_bytes(int64_t rows, int64_t K, int layout) {
+    if (rows < 0 || K < 0) return 0;
+    const int64_t Kp = (layout == GGB_Q8_1) ? (K + 511) / 512 * 512 : (K - K % 512 + 512);
+    return rows * (Kp / 32) * 36;
+}
+
+int ggb_quantize_q8_1(const void *X, int x_dtype, int64_t rows, int64_t K, void *out, int layout, int wtype,
+                      void *stream) {
+    g_err[0] = 0;
+    if (!check_dtype("ggb_quantize_q8_1", x_dtype)) return GGB_E_DTYPE;
+    if (layout != GGB_Q8_1 && layout != GGB_Q8_1_MMQ) {
+        ggb_set_error("ggb_quantize_q8_1: unknown layout %d", layout);
+        return GGB_E_ARG;
+    }
+    if (rows < 0 || K < 0) {
+        ggb_set_error("ggb_quantize_q8_1: negative shape");
+        return GGB_E_SHAPE;
+    }
+    if (rows == 0) return GGB_OK;
+    if (!out || (K > 0 && !X)) {
+        ggb_set_error("ggb_quantize_q8_1: null pointer");
+        return GGB_E_ARG;
+    }
+    if (reinterpret_cast<uintptr_t>(out) & 15) {
+        ggb_set_error("ggb_quantize_q8_1: out must be 16-byte aligned");
+        return GGB_E_ARG;
+    }
+    return ggb_quantize_q8_1_impl(X, x_dtype, rows, K, out, layout, wtype, static_cast<cudaStream_t>(stream));
+}
+
+static int check_matmul(const char *fn, const void *W, const void *X, const void *Y, int type, int dt,
+                        int64_t rows, int64_t K, int64_t N) {
+    if (!check_type(fn, type)) return GGB_E_TYPE;
+    if (!check_dtype(fn, dt)) return GGB_E_DTYPE;
+    if (rows < 0 || N < 0 || K <= 0 || K % block_elems(type) != 0) {
+        ggb_set_error("%s: K=%lld must be a positive multiple of the %d-value block", fn, (long long)K,
+                      block_elems(type));
+        return GGB_E_SHAPE;
+    }
+    if (rows == 0 || N == 0) return 1;          // nothing to do
+    if (!W || !X || !Y) {
+        ggb_set_error("%s: null pointer", fn);
+        return GGB_E_ARG;
+    }
+    if ((reinterpret_cast<uintptr_t>(W) & 1) || (reinterpret_cast<uintptr_t>(X) & 3) ||
+        (reinterpret_cast<uintptr_t>(Y) & 3)) {
+        ggb_set_error("%s: W must be 2-byte aligned, X and Y 4-byte aligned", fn);
+        return GGB_E_ARG;
+    }
+    return GGB_OK;
+}
+
+int64_t ggb_mmvq_workspace_bytes(int type, int64_t B, int64_t K, int64_t N) {
+    if (block_elems(type) == 0 || B <= 0 || K <= 0 || N <= 0) return 0;
+    return ggb_mmvq_workspace_bytes_impl(type, B, K, N);
+}
+
+int ggb_mmvq(const void *W, const void *X, void *Y, int type, int xy_dtype, int64_t B, int64_t K, int64_t N,
+             void *ws, int64_t ws_bytes, void *stream) {
+    g_err[0] = 0;
+    const int rc = check_matmul("ggb_mmvq", W, X, Y, type, xy_dtype, B, K, N);
+    if (rc < 0) return rc;
+    if (rc > 0) return GGB_OK;
+    if (B > 8) {
+        ggb_set_error("ggb_mmvq: batch %lld > 8 (use ggb_mmq)", (long long)B);
+        return GGB_E_SHAPE;
+    }
+    if (ggb_mmvq_workspace_bytes(type, B, K, N) > ws_bytes || (ws_bytes > 0 && !ws)) {
+        ggb_set_error("ggb_mmvq: workspace too small (%lld < %lld)", (long long)ws_bytes,
+                      (long long)ggb_mmvq_workspace_bytes(type, B, K, N));
+        return GGB_E_ARG;
+    }
+    return ggb_mmvq_impl(W, X, Y, type, xy_dtype, B, K, N, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int64_t ggb_mmq_workspace_bytes(int type, int64_t M, int64_t K, int64_t N) {
+    if (block_elems(type) == 0 || M <= 0 || K <= 0 || N <= 0) return 0;
+    return ggb_mmq_workspace_bytes_impl(type, M, K, N);
+}
+
+int ggb_mmq(const void *W, const void *X, void *Y, int type, int xy_dtype, int64_t M, int64_t K, int64_t N,
+            int64_t ldy, void *ws, int64_t ws_bytes, void *stream) {
+    g_err[0] = 0;
+    const int rc = check_matmul("ggb_mmq", W, X, Y, type, xy_dtype, M, K, N);
+    if (rc < 0) return rc;
+    if (rc > 0) return GGB_OK;
+    if (ldy < N) {
+        ggb_set_error("ggb_mmq: ldy=%lld < N=%lld", (long long)ldy, (long long)N);
+        return GGB_E_SHAPE;
+    }
+    const int64_t need = ggb_mmq_workspace_bytes(type, M, K, N);
+    if (need > ws_bytes || !ws || (reinterpret_cast<uintptr_t>(ws) & 255)) {
+        ggb_set_error("ggb_mmq: workspace must be 256-byte aligned and >= %lld bytes (got %lld)", (long long)need,
+                      (long long)ws_bytes);
+        return GGB_E_ARG;
+    }
+    return ggb_mmq_impl(W, X, Y, type, xy_dtype, M, K, N, ldy, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,159 @@
+// ggb_common.cuh -- shared device/host helpers for libggml_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include "../../include/ggml_b200.h"
+
+// ---------------------------------------------------------------- ggml type ids (ggml-common.h:1128-1161)
+enum : int {
+    T_Q4_0 = 2, T_Q4_1 = 3, T_Q5_0 = 6, T_Q5_1 = 7, T_Q8_0 = 8,
+    T_Q2_K = 10, T_Q3_K = 11, T_Q4_K = 12, T_Q5_K = 13, T_Q6_K = 14
+};
+
+template <int TYPE> struct BlockTraits;
+template <> struct BlockTraits<T_Q4_0> { static constexpr int QK = 32,  BS = 18;  };
+template <> struct BlockTraits<T_Q4_1> { static constexpr int QK = 32,  BS = 20;  };
+template <> struct BlockTraits<T_Q5_0> { static constexpr int QK = 32,  BS = 22;  };
+template <> struct BlockTraits<T_Q5_1> { static constexpr int QK = 32,  BS = 24;  };
+template <> struct BlockTraits<T_Q8_0> { static constexpr int QK = 32,  BS = 34;  };
+template <> struct BlockTraits<T_Q2_K> { static constexpr int QK = 256, BS = 84;  };
+template <> struct BlockTraits<T_Q3_K> { static constexpr int QK = 256, BS = 110; };
+template <> struct BlockTraits<T_Q4_K> { static constexpr int QK = 256, BS = 144; };
+template <> struct BlockTraits<T_Q5_K> { static constexpr int QK = 256, BS = 176; };
+template <> struct BlockTraits<T_Q6_K> { static constexpr int QK = 256, BS = 210; };
+
+// ---------------------------------------------------------------- host-side error plumbing (api.cu owns the storage)
+void ggb_set_error(const char *fmt, ...);
+
+#define GGB_CUDA_TRY(expr)                                                              \
+    do {                                                                                \
+        cudaError_t _e = (expr);                                                        \
+        if (_e != cudaSuccess) {                                                        \
+            ggb_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return GGB_E_CUDA;                                                          \
+        }                                                                               \
+    } while (0)
+
+struct DeviceInfo {
+    int sm_count;
+    int max_smem_optin;
+};
+// cached per device after the first call (the reference re-queries on every launch, mmq.cu:17-54)
+const DeviceInfo &ggb_device_info();
+
+// ---------------------------------------------------------------- small device helpers
+__device__ __forceinline__ float ggb_h2f(uint16_t bits) {
+    return __half2float(__ushort_as_half(bits));          // exact widening
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// 2-byte-aligned little-endian reads from shared or global memory
+__device__ __forceinline__ uint32_t ld_u16(const uint8_t *p) {
+    return *reinterpret_cast<const uint16_t *>(p);
+}
+__device__ __forceinline__ uint32_t ld_u32_a2(const uint8_t *p) {   // 2-byte aligned
+    return ld_u16(p) | (ld_u16(p + 2) << 16);
+}
+__device__ __forceinline__ uint32_t ld_u32_a4(const uint8_t *p) {   // 4-byte aligned
+    return *reinterpret_cast<const uint32_t *>(p);
+}
+
+// ---------------------------------------------------------------- output conversion: ONE round-to-nearest from fp32
+template <typename T> struct OutCvt;
+template <> struct OutCvt<float> {
+    static constexpr int DT = GGB_F32;
+};
+template <> struct OutCvt<__half> {
+    static constexpr int DT = GGB_F16;
+};
+template <> struct OutCvt<__nv_bfloat16> {
+    static constexpr int DT = GGB_BF16;
+};
+
+__device__ __forceinline__ uint32_t pack2(float a, float b, __half *) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b, __nv_bfloat16 *) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+
+// store 8 consecutive outputs (16-byte aligned destination)
+__device__ __forceinline__ void store8(float *dst, const float (&v)[8]) {
+    reinterpret_cast<float4 *>(dst)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4 *>(dst)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <typename T>
+__device__ __forceinline__ void store8(T *dst, const float (&v)[8]) {
+    uint4 u;
+    u.x = pack2(v[0], v[1], (T *)nullptr);
+    u.y = pack2(v[2], v[3], (T *)nullptr);
+    u.z = pack2(v[4], v[5], (T *)nullptr);
+    u.w = pack2(v[6], v[7], (T *)nullptr);
+    *reinterpret_cast<uint4 *>(dst) = u;
+}
+
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// ---------------------------------------------------------------- mbarrier + bulk-copy (TMA 1-D) PTX
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) { }
+}
+// global -> shared::cta bulk copy, completion counted on `bar`.  16-byte aligned src/dst, bytes % 16 == 0.
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// same with an L2 evict-first policy: weights/blocks that are streamed exactly once
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar,
+                                              uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}

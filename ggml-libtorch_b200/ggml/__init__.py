@@ -1,0 +1,227 @@
+"""`ggml` -- drop-in for the reference's torch custom-op package (torch-ext/ggml/__init__.py:15-44).
+
+Same three public functions, same positional signatures:
+
+    ggml_dequantize(W, quant_type, m, n)            -> Tensor [m, n]     (fp16; `dtype=` extension)
+    ggml_mul_mat_vec_a8(W, X, quant_type, row)      -> Tensor [B, row]   (MMVQ, 1 <= B <= 8)
+    ggml_mul_mat_a8(W, X, quant_type, row)          -> Tensor [..., row] (MMQ, X 2-D or 3-D)
+
+The ops are registered with torch.library (namespace `ggml_b200`, CUDA only, with fake kernels so
+meta tracing works) and call hand-written sm_100a CUDA through the C ABI of libggml_b200.so
+(include/ggml_b200.h).  PyTorch supplies device memory and streams only.  There is no CPU path:
+non-CUDA tensors raise.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _capi
+from ._capi import GGB_BF16, GGB_F16, GGB_F32, GGB_Q8_1, GGB_Q8_1_MMQ, GgmlB200Error  # noqa: F401
+
+__all__ = [
+    "ggml_dequantize", "ggml_mul_mat_vec_a8", "ggml_mul_mat_a8", "ggml_quantize_q8_1",
+    "dequantize_out", "mul_mat_vec_a8_out", "mul_mat_a8_out", "mmq_workspace_bytes",
+    "block_elems", "block_bytes", "SUPPORTED_TYPES", "MMVQ_MAX_BATCH",
+]
+
+_lib = _capi.lib
+_DT = {torch.float32: GGB_F32, torch.float16: GGB_F16, torch.bfloat16: GGB_BF16}
+_DT_INV = {v: k for k, v in _DT.items()}
+
+# ggml_type ids, ggml/ggml-common.h:1128-1161
+SUPPORTED_TYPES = (2, 3, 6, 7, 8, 10, 11, 12, 13, 14)
+MMVQ_MAX_BATCH = 8
+
+
+def block_elems(quant_type: int) -> int:
+    return _lib.ggb_block_elems(int(quant_type))
+
+
+def block_bytes(quant_type: int) -> int:
+    return _lib.ggb_block_bytes(int(quant_type))
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _check_w(W: torch.Tensor, quant_type: int, rows: int, cols: int, what: str) -> None:
+    if not W.is_cuda:
+        raise ValueError(f"{what}: W must be a CUDA tensor (ggml-b200 has no CPU path)")
+    if W.dtype != torch.uint8:
+        raise ValueError(f"{what}: W must be uint8 raw GGUF bytes, got {W.dtype}")
+    if not W.is_contiguous():
+        raise ValueError(f"{what}: W must be contiguous")
+    qk, bs = block_elems(quant_type), block_bytes(quant_type)
+    if qk == 0:
+        raise ValueError(f"{what}: unsupported ggml quant type {int(quant_type)}")
+    if cols % qk != 0:
+        raise ValueError(f"{what}: {cols} columns is not a multiple of the {qk}-value block")
+    need = rows * (cols // qk) * bs
+    if W.numel() != need:
+        raise ValueError(f"{what}: W has {W.numel()} bytes, expected {need} for [{rows}, {cols}] of type {int(quant_type)}")
+
+
+# ------------------------------------------------------------------------------------------------
+# out-variants: no allocation, used by the custom ops below and by bench.py / CUDA-graph capture
+# ------------------------------------------------------------------------------------------------
+
+def dequantize_out(W: torch.Tensor, quant_type: int, m: int, n: int, out: torch.Tensor) -> torch.Tensor:
+    _check_w(W, quant_type, m, n, "ggml_dequantize")
+    if out.dtype not in _DT or not out.is_contiguous() or out.numel() != m * n or out.device != W.device:
+        raise ValueError("ggml_dequantize: out must be a contiguous fp32/fp16/bf16 tensor of m*n values on W's device")
+    with torch.cuda.device(W.device):
+        rc = _lib.ggb_dequantize(W.data_ptr(), int(quant_type), m, n, out.data_ptr(), _DT[out.dtype], _stream(W))
+    _capi.check(rc, "ggml_dequantize")
+    return out
+
+
+def q8_1_bytes(rows: int, K: int, layout: int) -> int:
+    return _lib.ggb_q8_1_bytes(rows, K, layout)
+
+
+def ggml_quantize_q8_1(X: torch.Tensor, layout: int = GGB_Q8_1, wtype: int = 12) -> torch.Tensor:
+    """q8_1 activation quantization as a standalone op (parity tests / MMQ producer).
+    layout GGB_Q8_1 -> uint8 [rows, Kp/32*36]; GGB_Q8_1_MMQ -> uint8 [Kp/128, rows, 144]."""
+    if not X.is_cuda or X.dtype not in _DT or X.dim() != 2 or not X.is_contiguous():
+        raise ValueError("ggml_quantize_q8_1: X must be a contiguous 2-D fp32/fp16/bf16 CUDA tensor")
+    rows, K = X.shape
+    nbytes = q8_1_bytes(rows, K, layout)
+    out = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=X.device)[:nbytes]
+    with torch.cuda.device(X.device):
+        rc = _lib.ggb_quantize_q8_1(X.data_ptr(), _DT[X.dtype], rows, K, out.data_ptr(), layout, int(wtype), _stream(X))
+    _capi.check(rc, "ggml_quantize_q8_1")
+    if layout == GGB_Q8_1:
+        return out.view(rows, -1)
+    return out.view(-1, rows, 144)
+
+
+def _check_x(X: torch.Tensor, W: torch.Tensor, what: str) -> None:
+    if not X.is_cuda or X.device != W.device:
+        raise ValueError(f"{what}: X must be a CUDA tensor on W's device")
+    if X.dtype not in _DT:
+        raise ValueError(f"{what}: X must be fp32, fp16 or bf16, got {X.dtype}")
+    if not X.is_contiguous():
+        raise ValueError(f"{what}: X must be contiguous")
+
+
+def mmvq_workspace_bytes(quant_type: int, B: int, K: int, N: int) -> int:
+    return _lib.ggb_mmvq_workspace_bytes(int(quant_type), B, K, N)
+
+
+def mul_mat_vec_a8_out(W: torch.Tensor, X: torch.Tensor, quant_type: int, row: int, out: torch.Tensor,
+                       ws: torch.Tensor | None = None) -> torch.Tensor:
+    what = "ggml_mul_mat_vec_a8"
+    _check_x(X, W, what)
+    if X.dim() != 2:
+        raise ValueError(f"{what}: X must be [B, K]")
+    B, K = X.shape
+    if not 1 <= B <= MMVQ_MAX_BATCH:
+        raise ValueError(f"{what}: batch {B} outside 1..{MMVQ_MAX_BATCH} (use ggml_mul_mat_a8)")
+    _check_w(W, quant_type, row, K, what)
+    if out.dtype != X.dtype or not out.is_contiguous() or out.numel() != B * row or out.device != W.device:
+        raise ValueError(f"{what}: out must be a contiguous [B, row] tensor of X's dtype")
+    need = mmvq_workspace_bytes(quant_type, B, K, row)
+    if need and (ws is None or ws.numel() * ws.element_size() < need):
+        ws = torch.empty(need, dtype=torch.uint8, device=W.device)
+    with torch.cuda.device(W.device):
+        rc = _lib.ggb_mmvq(W.data_ptr(), X.data_ptr(), out.data_ptr(), int(quant_type), _DT[X.dtype], B, K, row,
+                           ws.data_ptr() if ws is not None else None,
+                           ws.numel() * ws.element_size() if ws is not None else 0, _stream(W))
+    _capi.check(rc, what)
+    return out
+
+
+def mmq_workspace_bytes(quant_type: int, M: int, K: int, N: int) -> int:
+    return _lib.ggb_mmq_workspace_bytes(int(quant_type), M, K, N)
+
+
+def mul_mat_a8_out(W: torch.Tensor, X2d: torch.Tensor, quant_type: int, row: int, out: torch.Tensor,
+                   ws: torch.Tensor | None = None, ldy: int | None = None) -> torch.Tensor:
+    what = "ggml_mul_mat_a8"
+    _check_x(X2d, W, what)
+    if X2d.dim() != 2:
+        raise ValueError(f"{what}: X must be flattened to [M, K]")
+    M, K = X2d.shape
+    _check_w(W, quant_type, row, K, what)
+    ldy = row if ldy is None else ldy
+    if out.dtype != X2d.dtype or out.device != W.device:
+        raise ValueError(f"{what}: out must have X's dtype and device")
+    need = mmq_workspace_bytes(quant_type, M, K, row)
+    if ws is None or ws.numel() * ws.element_size() < need:
+        ws = torch.empty(max(need, 256), dtype=torch.uint8, device=W.device)
+    with torch.cuda.device(W.device):
+        rc = _lib.ggb_mmq(W.data_ptr(), X2d.data_ptr(), out.data_ptr(), int(quant_type), _DT[X2d.dtype], M, K, row,
+                          ldy, ws.data_ptr(), ws.numel() * ws.element_size(), _stream(W))
+    _capi.check(rc, what)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# torch.library registration (schemas follow torch-ext/torch_binding.cpp:6-21)
+# ------------------------------------------------------------------------------------------------
+
+@torch.library.custom_op("ggml_b200::ggml_dequantize", mutates_args=(), device_types="cuda")
+def _op_dequantize(W: torch.Tensor, type: int, m: int, n: int, out_dtype: int) -> torch.Tensor:
+    out = torch.empty((m, n), dtype=_DT_INV[out_dtype], device=W.device)
+    return dequantize_out(W, type, m, n, out)
+
+
+@_op_dequantize.register_fake
+def _(W, type, m, n, out_dtype):
+    return torch.empty((m, n), dtype=_DT_INV[out_dtype], device=W.device)
+
+
+@torch.library.custom_op("ggml_b200::ggml_mul_mat_vec_a8", mutates_args=(), device_types="cuda")
+def _op_mmvq(W: torch.Tensor, X: torch.Tensor, type: int, row: int) -> torch.Tensor:
+    out = torch.empty((X.shape[0], row), dtype=X.dtype, device=W.device)
+    return mul_mat_vec_a8_out(W, X, type, row, out)
+
+
+@_op_mmvq.register_fake
+def _(W, X, type, row):
+    return torch.empty((X.shape[0], row), dtype=X.dtype, device=W.device)
+
+
+@torch.library.custom_op("ggml_b200::ggml_mul_mat_a8", mutates_args=(), device_types="cuda")
+def _op_mmq(W: torch.Tensor, X: torch.Tensor, type: int, row: int) -> torch.Tensor:
+    # X 2-D [M, K] or 3-D [B, T, K] flattened to B*T rows, as ggml/mmq.cu:183-204
+    if X.dim() not in (2, 3):
+        raise ValueError("ggml_mul_mat_a8: X must be 2-D or 3-D")
+    lead = X.shape[:-1]
+    X2 = X.reshape(-1, X.shape[-1])
+    out = torch.empty((X2.shape[0], row), dtype=X.dtype, device=W.device)
+    mul_mat_a8_out(W, X2, type, row, out)
+    return out.view(*lead, row)
+
+
+@_op_mmq.register_fake
+def _(W, X, type, row):
+    return torch.empty((*X.shape[:-1], row), dtype=X.dtype, device=W.device)
+
+
+# ------------------------------------------------------------------------------------------------
+# public functions (reference names and positional signatures)
+# ------------------------------------------------------------------------------------------------
+
+def ggml_dequantize(W: torch.Tensor, quant_type: int, m: int, n: int, dtype: torch.dtype | None = None) -> torch.Tensor:
+    """Dequantize the GGML tensor.  fp16 output like the reference CUDA op (ggml/ggml_kernel.cu:71-73);
+    `dtype=` (fp32/fp16/bf16) fuses the cast the reference's callers do afterwards."""
+    dtype = torch.float16 if dtype is None else dtype
+    if dtype not in _DT:
+        raise ValueError(f"ggml_dequantize: unsupported output dtype {dtype}")
+    _check_w(W, quant_type, int(m), int(n), "ggml_dequantize")
+    return torch.ops.ggml_b200.ggml_dequantize(W, int(quant_type), int(m), int(n), _DT[dtype])
+
+
+def ggml_mul_mat_vec_a8(W: torch.Tensor, X: torch.Tensor, quant_type: int, row: int) -> torch.Tensor:
+    """Mulmat with the MMVQ kernel.  The reference requires batch_size == 1; here 1 <= batch <= 8."""
+    batch = X.size(0)
+    if not 1 <= batch <= MMVQ_MAX_BATCH:
+        raise ValueError(f"Batch size must be 1..{MMVQ_MAX_BATCH} for the MMVQ kernel, got {batch}")
+    return torch.ops.ggml_b200.ggml_mul_mat_vec_a8(W, X, int(quant_type), int(row))
+
+
+def ggml_mul_mat_a8(W: torch.Tensor, X: torch.Tensor, quant_type: int, row: int) -> torch.Tensor:
+    """Mulmat through the MMQ kernel for arbitrary batch size."""
+    return torch.ops.ggml_b200.ggml_mul_mat_a8(W, X, int(quant_type), int(row))

@@ -1,0 +1,103 @@
+/*
+ * ggml_b200.h -- C ABI of libggml_b200.so: the GGUF quantized-weight hot path (dequantize, q8_1
+ * activation quantization, MMVQ, MMQ) as hand-written sm_100a CUDA.
+ *
+ * This is the drop-in boundary.  Each entry point replaces one host launcher of the reference
+ * (paths relative to /root/reference/hf-kernels/ggml-kernels unless noted); the reference-side
+ * binding a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer borrowed for the call;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); work is enqueued
+ *     asynchronously, nothing synchronises, nothing allocates -> CUDA-graph capturable;
+ *   - the caller has made the right device current (the reference uses OptionalCUDAGuard,
+ *     ggml/ggml_kernel.cu:70,85);
+ *   - return value 0 = enqueued; negative = GGB_E_* and ggb_last_error() (thread-local) says why.
+ *     Nothing throws or exits across the ABI (the reference printf+exit()s, ggml/cuda_utils.h:19-27).
+ *   - `type` is a ggml_type id (ggml/ggml-common.h:1128-1161): Q4_0=2 Q4_1=3 Q5_0=6 Q5_1=7 Q8_0=8
+ *     Q2_K=10 Q3_K=11 Q4_K=12 Q5_K=13 Q6_K=14.
+ *   - dtype codes: GGB_F32=0, GGB_F16=1, GGB_BF16=2.
+ */
+#ifndef GGML_B200_H
+#define GGML_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GGB_VERSION 100
+
+enum ggb_dtype { GGB_F32 = 0, GGB_F16 = 1, GGB_BF16 = 2 };
+
+enum ggb_status {
+    GGB_OK = 0,
+    GGB_E_TYPE = -1,      /* unsupported ggml_type */
+    GGB_E_SHAPE = -2,     /* shape not divisible by the block size / out of range */
+    GGB_E_DTYPE = -3,     /* unsupported dtype code */
+    GGB_E_ARG = -4,       /* null pointer, misalignment, workspace too small */
+    GGB_E_CUDA = -5       /* a CUDA runtime call or launch failed */
+};
+
+enum ggb_q8_layout {
+    GGB_Q8_1 = 0,         /* rows of block_q8_1 (36 B), K padded to ceil(K/512)*512  -- MMVQ operand */
+    GGB_Q8_1_MMQ = 1      /* block_q8_1_mmq (144 B), chunk-major, K padded to K-K%512+512 -- MMQ operand */
+};
+
+int         ggb_version(void);
+/* Thread-local description of the last failure on this thread ("" if none). */
+const char *ggb_last_error(void);
+
+/* Block geometry of a ggml_type (0 if unsupported).  ggml/ggml-common.h:1163-1240 (qk) / :17-108. */
+int         ggb_block_elems(int type);
+int         ggb_block_bytes(int type);
+
+/*
+ * Dequantize W (raw GGUF bytes, uint8 [m, n/QK*block_bytes], row-major contiguous) into out [m, n].
+ * Replaces ggml_dequantize (ggml/ggml_kernel.cu:68-78) + ggml_get_to_fp16_cuda (ggml/dequantize.cuh:525-568)
+ * and, for fp32 output, the CPU op /root/reference/ggml-cpu/custom_ops.cpp:11-36.
+ * Arithmetic is the CPU op's fp32 order (separately rounded mul then add/sub) followed by ONE
+ * round-to-nearest conversion to out_dtype, so fp32 output is bit-identical to the CPU op and
+ * fp16/bf16 output equals torch's .to(dtype) of it.  (The reference CUDA op computes in half.)
+ */
+int         ggb_dequantize(const void *W, int type, int64_t m, int64_t n,
+                           void *out, int out_dtype, void *stream);
+
+/*
+ * q8_1 activation quantization of X [rows, K] (x_dtype, contiguous).
+ * layout GGB_Q8_1     replaces quantize_row_q8_1_cuda   (ggml/ggml_kernel.cu:13-66)
+ * layout GGB_Q8_1_MMQ replaces quantize_mmq_q8_1_cuda   (ggml/mmq.cu:109-177); `wtype` selects
+ *                     need_sum (ds = half2(d,sum)) vs fp32 d as mmq_need_sum does (ggml/mmq.cu:84-106).
+ * `out` must hold ggb_q8_1_bytes(rows, K, layout) bytes.
+ */
+int64_t     ggb_q8_1_bytes(int64_t rows, int64_t K, int layout);
+int         ggb_quantize_q8_1(const void *X, int x_dtype, int64_t rows, int64_t K,
+                              void *out, int layout, int wtype, void *stream);
+
+/*
+ * MMVQ: Y[B, N] = q8_1(X[B, K]) . W[N, K]^T, 1 <= B <= 8 (the reference allows B == 1 only).
+ * Replaces ggml_mul_mat_vec_a8 (ggml/ggml_kernel.cu:80-193): quantize_row_q8_1_cuda + mul_mat_vec_q
+ * (ggml/mmvq.cuh:2-38) in ONE launch -- activations are quantized to q8_1 inside the kernel.
+ * X and Y share `xy_dtype`.  No workspace is needed (ws may be NULL); the query returns 0.
+ */
+int64_t     ggb_mmvq_workspace_bytes(int type, int64_t B, int64_t K, int64_t N);
+int         ggb_mmvq(const void *W, const void *X, void *Y, int type, int xy_dtype,
+                     int64_t B, int64_t K, int64_t N, void *ws, int64_t ws_bytes, void *stream);
+
+/*
+ * MMQ: Y[M, N] (row stride ldy elements) = q8_1_mmq(X[M, K]) . W[N, K]^T.
+ * Replaces ggml_mul_mat_a8 (ggml/mmq.cu:180-255): quantize_mmq_q8_1_cuda + mul_mat_q
+ * (ggml/mmq.cuh:1917-2031).  `ws` must hold ggb_mmq_workspace_bytes(...) bytes (the quantized
+ * activations; the reference allocates them with torch::empty on every call, ggml/mmq.cu:207-208).
+ */
+int64_t     ggb_mmq_workspace_bytes(int type, int64_t M, int64_t K, int64_t N);
+int         ggb_mmq(const void *W, const void *X, void *Y, int type, int xy_dtype,
+                    int64_t M, int64_t K, int64_t N, int64_t ldy,
+                    void *ws, int64_t ws_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GGML_B200_H */

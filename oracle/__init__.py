@@ -1,0 +1,189 @@
+"""numpy-facing ctypes wrapper of the CPU oracle.
+
+TEST INFRASTRUCTURE ONLY.  Importable from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs -- never from the product package (ggml-libtorch_b200/), which
+has no CPU fallback.  See oracle/ggml_oracle.c for what is restated and how it is pinned.
+"""
+from __future__ import annotations
+
+import ctypes
+import importlib.util
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "libggml_oracle.so")
+_REF_PATH = os.path.join(_HERE, "_ref", "custom_ops.so")
+
+Q4_0, Q4_1, Q5_0, Q5_1, Q8_0, Q8_1 = 2, 3, 6, 7, 8, 9
+Q2_K, Q3_K, Q4_K, Q5_K, Q6_K = 10, 11, 12, 13, 14
+LEGACY_TYPES = (Q4_0, Q4_1, Q5_0, Q5_1, Q8_0)
+K_TYPES = (Q2_K, Q3_K, Q4_K, Q5_K, Q6_K)
+ALL_TYPES = LEGACY_TYPES + K_TYPES
+TYPE_NAMES = {2: "Q4_0", 3: "Q4_1", 6: "Q5_0", 7: "Q5_1", 8: "Q8_0", 9: "Q8_1",
+              10: "Q2_K", 11: "Q3_K", 12: "Q4_K", 13: "Q5_K", 14: "Q6_K"}
+
+
+def build(force: bool = False) -> str:
+    """Compile oracle/ggml_oracle.c (gcc) if the shared object is missing or stale."""
+    src = os.path.join(_HERE, "ggml_oracle.c")
+    hdr = os.path.join(_HERE, "ggml_oracle.h")
+    stale = (not os.path.exists(_LIB_PATH)
+             or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(src), os.path.getmtime(hdr)))
+    if force or stale:
+        subprocess.run(["make", "-s", "-C", _HERE], check=True)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        L = ctypes.CDLL(_LIB_PATH)
+        i64, vp, ci = ctypes.c_int64, ctypes.c_void_p, ctypes.c_int
+        L.orc_block_elems.argtypes = [ci]
+        L.orc_block_bytes.argtypes = [ci]
+        L.orc_mmq_need_sum.argtypes = [ci]
+        L.orc_dequantize.argtypes = [vp, ci, i64, vp]
+        L.orc_dequantize_mt.argtypes = [vp, ci, i64, i64, vp]
+        L.orc_q8_1_row_bytes.argtypes = [i64]
+        L.orc_q8_1_row_bytes.restype = i64
+        L.orc_quantize_q8_1.argtypes = [vp, i64, i64, vp]
+        L.orc_q8_1_mmq_bytes.argtypes = [i64, i64]
+        L.orc_q8_1_mmq_bytes.restype = i64
+        L.orc_quantize_q8_1_mmq.argtypes = [vp, i64, i64, ci, vp]
+        L.orc_mmvq.argtypes = [vp, ci, vp, i64, i64, i64, vp]
+        L.orc_mmq.argtypes = [vp, ci, vp, i64, i64, i64, vp]
+        _lib = L
+    return _lib
+
+
+def block_elems(t: int) -> int:
+    return lib().orc_block_elems(int(t))
+
+
+def block_bytes(t: int) -> int:
+    return lib().orc_block_bytes(int(t))
+
+
+def mmq_need_sum(t: int) -> bool:
+    return bool(lib().orc_mmq_need_sum(int(t)))
+
+
+def _u8(a) -> np.ndarray:
+    a = np.ascontiguousarray(a)
+    return a.view(np.uint8).reshape(-1)
+
+
+def dequantize(w, qtype: int, m: int, n: int, threads: bool = False) -> np.ndarray:
+    """fp32 [m, n] from raw GGUF bytes; restates custom_ops.ggml_dequantize + gguf-py for K-quants."""
+    wb = _u8(w)
+    qtype = int(qtype)
+    need = m * n // block_elems(qtype) * block_bytes(qtype)
+    if wb.size != need:
+        raise ValueError(f"expected {need} bytes for [{m},{n}] {TYPE_NAMES.get(qtype)}, got {wb.size}")
+    out = np.empty((m, n), dtype=np.float32)
+    if threads:
+        rc = lib().orc_dequantize_mt(wb.ctypes.data, qtype, m, n, out.ctypes.data)
+    else:
+        rc = lib().orc_dequantize(wb.ctypes.data, qtype, m * n, out.ctypes.data)
+    if rc:
+        raise ValueError(f"orc_dequantize rc={rc}")
+    return out
+
+
+def quantize_q8_1(x: np.ndarray) -> np.ndarray:
+    """x fp32 [rows, K] -> uint8 [rows, Kp/32*36] (block_q8_1 rows, ggml_kernel.cu:13-66)."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    rows, K = x.shape
+    out = np.zeros((rows, lib().orc_q8_1_row_bytes(K)), dtype=np.uint8)
+    lib().orc_quantize_q8_1(x.ctypes.data, rows, K, out.ctypes.data)
+    return out
+
+
+def quantize_q8_1_mmq(x: np.ndarray, need_sum: bool) -> np.ndarray:
+    """x fp32 [M, K] -> uint8 [Kp/128, M, 144] (block_q8_1_mmq, chunk-major, mmq.cu:109-177)."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    M, K = x.shape
+    nbytes = lib().orc_q8_1_mmq_bytes(M, K)
+    out = np.zeros(nbytes, dtype=np.uint8)
+    lib().orc_quantize_q8_1_mmq(x.ctypes.data, M, K, int(bool(need_sum)), out.ctypes.data)
+    return out.reshape(-1, M, 144)
+
+
+def mmvq(w, qtype: int, x: np.ndarray, N: int) -> np.ndarray:
+    """Y[B,N] fp32 = MMVQ(W, q8_1(x)); x is the fp32-widened activation [B,K]."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    B, K = x.shape
+    q = quantize_q8_1(x)
+    wb = _u8(w)
+    y = np.empty((B, N), dtype=np.float32)
+    rc = lib().orc_mmvq(wb.ctypes.data, int(qtype), q.ctypes.data, B, K, N, y.ctypes.data)
+    if rc:
+        raise ValueError(f"orc_mmvq rc={rc}")
+    return y
+
+
+def mmq(w, qtype: int, x: np.ndarray, N: int) -> np.ndarray:
+    """Y[M,N] fp32 = MMQ(W, q8_1_mmq(x))."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    M, K = x.shape
+    q = quantize_q8_1_mmq(x, mmq_need_sum(qtype))
+    wb = _u8(w)
+    y = np.empty((M, N), dtype=np.float32)
+    rc = lib().orc_mmq(wb.ctypes.data, int(qtype), q.ctypes.data, M, K, N, y.ctypes.data)
+    if rc:
+        raise ValueError(f"orc_mmq rc={rc}")
+    return y
+
+
+def num_threads() -> int:
+    return lib().orc_num_threads()
+
+
+# ---------------------------------------------------------------- the reference's own CPU op
+
+_ref_mod = None
+
+
+def ref_custom_ops():
+    """The reference's `custom_ops` module compiled from /root/reference (oracle/_ref), or None."""
+    global _ref_mod
+    if _ref_mod is None:
+        if not os.path.exists(_REF_PATH):
+            try:
+                from . import build_ref
+                build_ref.build()
+            except Exception:
+                pass
+        if not os.path.exists(_REF_PATH):
+            return None
+        import torch  # noqa: F401  (the extension links against libtorch)
+        spec = importlib.util.spec_from_file_location("custom_ops", _REF_PATH)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        _ref_mod = mod
+    return _ref_mod
+
+
+# ---------------------------------------------------------------- synthetic GGUF weights
+
+def random_weights(qtype: int, rows: int, cols: int, seed: int = 0) -> np.ndarray:
+    """Random *valid* block bytes, uint8 [rows, cols/QK*bs] (SURVEY.md §8d 'C2' recipe):
+    all payload bytes uniform, fp16 scale fields = fp16(U(0.5,1.5) * 2^-10) with random sign off."""
+    qtype = int(qtype)
+    qk, bs = block_elems(qtype), block_bytes(qtype)
+    nb = rows * cols // qk
+    rng = np.random.default_rng(seed)
+    blocks = rng.integers(0, 256, size=(nb, bs), dtype=np.uint8)
+    half_offsets = {Q4_0: [0], Q4_1: [0, 2], Q5_0: [0], Q5_1: [0, 2], Q8_0: [0],
+                    Q2_K: [80, 82], Q3_K: [108], Q4_K: [0, 2], Q5_K: [0, 2], Q6_K: [208]}[qtype]
+    for off in half_offsets:
+        h = (rng.uniform(0.5, 1.5, size=nb) * 2.0 ** -10).astype(np.float16)
+        blocks[:, off:off + 2] = h.view(np.uint8).reshape(nb, 2)
+    return blocks.reshape(rows, cols // qk * bs)
