@@ -1,0 +1,116 @@
+"""The other two families of BASELINE.json's metric, reported under `extras` of bench.py's JSON line:
+
+  * MMVQ weight GB/s (BASELINE configs[2]: Llama-3-8B Q4_K/Q6_K decode GEMV shapes, batch 1..8) against
+    the measured HBM peak.  Each timed pass walks 8 distinct copies of the weight matrix (264-385 MB,
+    > 2x the 126 MB L2), replayed from a CUDA graph so the 5-10 us kernels are not launch-bound.
+  * MMQ int8 TOPS (BASELINE configs[3]: M = 512..8192 prefill tokens) against the int8 tensor peak.
+
+Called only from bench.py; uses the product package only (no oracle).
+"""
+from __future__ import annotations
+
+import statistics
+
+import torch
+
+NOMINAL_INT8_TOPS = 4500.0      # dense int8 tcgen05 peak of a B200 (2x the bf16 nominal of 2250)
+
+
+def _time_graph(fn, iters: int, warm: int = 3) -> float:
+    """Capture `fn` (a sequence of launches) into a CUDA graph, replay it, return ms per replay (median)."""
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        fn()                                  # first call outside capture: one-time function attributes
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            fn()
+        for _ in range(warm):
+            g.replay()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(iters):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(s)
+            g.replay()
+            b.record(s)
+            b.synchronize()
+            ts.append(a.elapsed_time(b))
+    torch.cuda.current_stream().wait_stream(s)
+    return statistics.median(ts)
+
+
+def mmvq_section(ggml, synth, dev, peaks, peak_kind):
+    hbm = float(peaks["hbm_gbs"])
+    out = {"unit": "GB/s (weight bytes / time)", "peak": hbm, "peak_source": peak_kind,
+           "method": "CUDA-graph replay over 8 distinct weight copies per pass (> 2x L2), median of 10 replays, fp16 x/y",
+           "cases": []}
+    ncopies = 8
+    launches = 0
+    for tname, t in (("Q4_K", 12), ("Q6_K", 14)):
+        for (N, K) in ((14336, 4096), (4096, 14336)):
+            if t == 14 and N == 14336:
+                continue                     # Q4_K_M stores ffn_down (4096 x 14336) in Q6_K; gate/up stay Q4_K
+            base = torch.from_numpy(synth.random_blocks(t, N, K, seed=N + t)).to(dev)
+            copies = [base] + [base.clone() for _ in range(ncopies - 1)]
+            wbytes = base.numel()
+            for B in (1, 2, 4, 8):
+                x = torch.randn(B, K, dtype=torch.float16, device=dev)
+                y = torch.empty(B, N, dtype=torch.float16, device=dev)
+
+                def run():
+                    for w in copies:
+                        ggml.mul_mat_vec_a8_out(w, x, t, N, y)
+
+                ms = _time_graph(run, iters=10)
+                launches += ncopies * 14
+                gbs = wbytes * ncopies / (ms * 1e-3) / 1e9
+                out["cases"].append({"type": tname, "N": N, "K": K, "B": B, "us_per_launch": ms * 1e3 / ncopies,
+                                     "weight_GBps": gbs, "frac_of_hbm_peak": gbs / hbm})
+            del copies, base
+    return out, launches
+
+
+def mmq_section(ggml, synth, dev, peaks, peak_kind):
+    out = {"unit": "TOPS (2*M*N*K / time)", "peak": NOMINAL_INT8_TOPS,
+           "peak_source": "nominal dense int8 (no measured int8 peak in MEASURED_PEAKS.json)",
+           "bf16_measured_tflops": peaks.get("bf16_tflops"),
+           "method": "CUDA events around 10 launches after 3 warm-ups, fp16 x/y, workspace preallocated", "cases": []}
+    launches = 0
+    for tname, t in (("Q4_K", 12), ("Q6_K", 14)):
+        N, K = 14336, 4096
+        w = torch.from_numpy(synth.random_blocks(t, N, K, seed=1)).to(dev)
+        for M in (512, 1024, 2048, 4096, 8192):
+            x = torch.randn(M, K, dtype=torch.float16, device=dev)
+            y = torch.empty(M, N, dtype=torch.float16, device=dev)
+            ws = torch.empty(max(ggml.mmq_workspace_bytes(t, M, K, N), 256), dtype=torch.uint8, device=dev)
+            for _ in range(3):
+                ggml.mul_mat_a8_out(w, x, t, N, y, ws)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            iters = 10
+            a.record()
+            for _ in range(iters):
+                ggml.mul_mat_a8_out(w, x, t, N, y, ws)
+            b.record()
+            b.synchronize()
+            ms = a.elapsed_time(b) / iters
+            launches += iters + 3
+            tops = 2.0 * M * N * K / (ms * 1e-3) / 1e12
+            out["cases"].append({"type": tname, "M": M, "N": N, "K": K, "ms": ms, "TOPS": tops,
+                                 "frac_of_int8_peak": tops / NOMINAL_INT8_TOPS})
+    return out, launches
+
+
+def run(ggml, synth, dev, rank, world, peaks, peak_kind):
+    extras = {}
+    n = 0
+    if rank == 0:
+        for name, fn in (("mmvq", mmvq_section), ("mmq", mmq_section)):
+            try:
+                extras[name], k = fn(ggml, synth, dev, peaks, peak_kind)
+                n += k
+            except Exception as e:
+                extras[name] = {"error": f"{type(e).__name__}: {e}"}
+    return extras, n

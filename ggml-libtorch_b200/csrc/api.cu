@@ -37,6 +37,7 @@ const DeviceInfo &ggb_device_info() {
     if (dev < 0 || dev >= 64) dev = 0;
     std::call_once(once[dev], [dev]() {
         int v = 0;
+        info[dev].dev = dev;
         cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
         info[dev].sm_count = v > 0 ? v : 148;
         cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);

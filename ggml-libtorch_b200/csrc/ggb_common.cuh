@@ -39,6 +39,7 @@ void ggb_set_error(const char *fmt, ...);
     } while (0)
 
 struct DeviceInfo {
+    int dev;             // CUDA device ordinal (0..63), index for per-device one-time function attributes
     int sm_count;
     int max_smem_optin;
 };

@@ -1,6 +1,502 @@
-// placeholder replaced by the real kernel
-#include "ggb_common.cuh"
+// mmvq.cu -- quantized GEMV for decode batches 1..8 (MMVQ) on sm_100a.
+//
+// Replaces ggml_mul_mat_vec_a8 = quantize_row_q8_1_cuda + mul_mat_vec_q + the per-type vec_dot_*_q8_1
+// (hf-kernels/ggml-kernels/ggml/ggml_kernel.cu:13-66, 80-193; ggml/mmvq.cuh:2-209; ggml/vecdotq.cuh:45-605).
+// The reference runs two kernels (quantize, then one 32-thread CTA per weight row with 2/4-byte loads)
+// and is limited to batch 1.  This is ONE launch:
+//
+//   * prologue: the CTA quantizes the B x K activations to q8_1 in shared memory (int8 quants, the
+//     fp16-rounded scale d and, per weight type, the fp16-rounded sum s or the integer half-sums of
+//     the quants) -- bit-identical to quantize_q8_1 (q8_1.cuh);
+//   * weight streaming: one CTA per SM owns a contiguous, byte-balanced range of weight rows.  A
+//     producer warp moves (32 rows x 2048-column) stages of raw GGUF bytes into a shared-memory ring
+//     with cp.async.bulk (TMA engine, mbarrier completion, L2 evict-first): no per-thread load
+//     instructions, 100-200 KB in flight per SM;
+//   * compute: 16 consumer warps, two rows per warp (each activation word fetched from shared memory
+//     is used for both rows), one lane per 32-value group: raw quants unpacked in registers, __dp4a
+//     integer dots, fp32 scale/min algebra in the reference's per-type form, warp-shuffle reduction.
+//
+// Algorithmic bytes per launch: N*K/QK*block_bytes (weights, streamed once).  Tolerance contract
+// (tests/test_gpu_mmvq.py): integer dots are exact; only the fp32 summation order differs from the
+// reference, so results agree with the oracle to ~1e-6 relative of the output scale.
+#include "q8_1.cuh"
+
+namespace {
+
+constexpr int kConsumerWarps = 16;
+constexpr int kThreads = (kConsumerWarps + 1) * 32;
+constexpr int kRowsPerWarp = 2;
+constexpr int kStageRows = kConsumerWarps * kRowsPerWarp;       // 32
+constexpr int kChunkElems = 2048;                               // columns per stage
+constexpr int kChunkGroups = kChunkElems / 32;
+constexpr int kMaxStages = 8;
+
+struct Params {
+    const uint8_t *W;
+    const void *X;
+    void *Y;
+    int64_t N;
+    int K;
+    int row_bytes;       // K / QK * BS
+    int chunk_bytes;     // kChunkElems / QK * BS
+    int nchunks;
+    int seg_stride;      // shared-memory bytes per staged row segment (multiple of 16)
+    int nstages;
+    int fast;            // rows and segments are 16-byte aligned: TMA bulk copies
+    int x_vec;           // X is 16-byte aligned
+    int off_scales;      // byte offsets into dynamic shared memory
+    int off_stages;
+    int off_bars;
+};
+
+// ---------------------------------------------------------------- per-type traits
+template <int TYPE> struct VqTraits;
+//   NEED_SQ : aux = (int16 sq1 << 16 | int16 sq0), the sums of the q8 quants over each 16-value half
+//   NEED_S8 : aux = bits of the fp16-rounded float sum of the raw inputs (block_q8_1.s)
+template <> struct VqTraits<T_Q4_0> { static constexpr bool NEED_SQ = false, NEED_S8 = true;  };
+template <> struct VqTraits<T_Q4_1> { static constexpr bool NEED_SQ = false, NEED_S8 = true;  };
+template <> struct VqTraits<T_Q5_0> { static constexpr bool NEED_SQ = false, NEED_S8 = true;  };
+template <> struct VqTraits<T_Q5_1> { static constexpr bool NEED_SQ = false, NEED_S8 = true;  };
+template <> struct VqTraits<T_Q8_0> { static constexpr bool NEED_SQ = false, NEED_S8 = false; };
+template <> struct VqTraits<T_Q2_K> { static constexpr bool NEED_SQ = true,  NEED_S8 = false; };
+template <> struct VqTraits<T_Q3_K> { static constexpr bool NEED_SQ = true,  NEED_S8 = false; };
+template <> struct VqTraits<T_Q4_K> { static constexpr bool NEED_SQ = true,  NEED_S8 = false; };
+template <> struct VqTraits<T_Q5_K> { static constexpr bool NEED_SQ = true,  NEED_S8 = false; };
+template <> struct VqTraits<T_Q6_K> { static constexpr bool NEED_SQ = true,  NEED_S8 = false; };
+
+struct GroupW {
+    uint32_t w[8];      // the 32 raw quants of the group, 4 per word, element order
+    float a0, a1;       // scale of elements 0..15 / 16..31 (super-block d already applied)
+    float m0, m1;       // minima (dmin applied) or, for Q4_1/Q5_1, m0 = block minimum
+};
+
+__device__ __forceinline__ uint32_t spread4(uint32_t x) {       // bit i of x -> bit 4 of byte i
+    return ((x * 0x00204081u) & 0x01010101u) << 4;
+}
+__device__ __forceinline__ void k4_scale_min(int j, const uint8_t *s, int &sc, int &mn) {   // dequantize.cuh:154-161
+    if (j < 4) {
+        sc = s[j] & 63;
+        mn = s[j + 4] & 63;
+    } else {
+        sc = (s[j + 4] & 0x0f) | ((s[j - 4] >> 6) << 4);
+        mn = (s[j + 4] >> 4) | ((s[j] >> 6) << 4);
+    }
+}
+__device__ __forceinline__ int q3k_scale(const uint8_t *s, int is) {
+    const int lo = (is < 8) ? (s[is] & 0x0f) : (s[is - 8] >> 4);
+    const int hi = (s[8 + (is & 3)] >> (2 * (is >> 2))) & 3;
+    return (lo | (hi << 4)) - 32;
+}
+
+// Unpack group `g` (32 values) of a staged row segment that starts on a block boundary.
+template <int TYPE>
+__device__ __forceinline__ void load_group(const uint8_t *seg, int g, GroupW &o) {
+    constexpr int BS = BlockTraits<TYPE>::BS;
+    o.m0 = o.m1 = 0.0f;
+    if constexpr (TYPE == T_Q4_0) {
+        const uint8_t *b = seg + g * BS;
+        o.a0 = o.a1 = ggb_h2f(ld_u16(b));
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t q = ld_u32_a2(b + 2 + 4 * i);
+            o.w[i] = q & 0x0f0f0f0fu;
+            o.w[4 + i] = (q >> 4) & 0x0f0f0f0fu;
+        }
+    } else if constexpr (TYPE == T_Q4_1) {
+        const uint8_t *b = seg + g * BS;
+        o.a0 = o.a1 = ggb_h2f(ld_u16(b));
+        o.m0 = ggb_h2f(ld_u16(b + 2));
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t q = ld_u32_a4(b + 4 + 4 * i);
+            o.w[i] = q & 0x0f0f0f0fu;
+            o.w[4 + i] = (q >> 4) & 0x0f0f0f0fu;
+        }
+    } else if constexpr (TYPE == T_Q5_0) {
+        const uint8_t *b = seg + g * BS;
+        o.a0 = o.a1 = ggb_h2f(ld_u16(b));
+        const uint32_t qh = ld_u32_a2(b + 2);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t q = ld_u32_a2(b + 6 + 4 * i);
+            o.w[i] = (q & 0x0f0f0f0fu) | spread4((qh >> (4 * i)) & 0xf);
+            o.w[4 + i] = ((q >> 4) & 0x0f0f0f0fu) | spread4((qh >> (16 + 4 * i)) & 0xf);
+        }
+    } else if constexpr (TYPE == T_Q5_1) {
+        const uint8_t *b = seg + g * BS;
+        o.a0 = o.a1 = ggb_h2f(ld_u16(b));
+        o.m0 = ggb_h2f(ld_u16(b + 2));
+        const uint32_t qh = ld_u32_a4(b + 4);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t q = ld_u32_a4(b + 8 + 4 * i);
+            o.w[i] = (q & 0x0f0f0f0fu) | spread4((qh >> (4 * i)) & 0xf);
+            o.w[4 + i] = ((q >> 4) & 0x0f0f0f0fu) | spread4((qh >> (16 + 4 * i)) & 0xf);
+        }
+    } else if constexpr (TYPE == T_Q8_0) {
+        const uint8_t *b = seg + g * BS;
+        o.a0 = o.a1 = ggb_h2f(ld_u16(b));
+#pragma unroll
+        for (int i = 0; i < 8; i++) o.w[i] = ld_u32_a2(b + 2 + 4 * i);
+    } else if constexpr (TYPE == T_Q2_K) {
+        const uint8_t *b = seg + (g >> 3) * BS;
+        const int j = g & 7, n = j >> 2, s = j & 3;
+        const float d = ggb_h2f(ld_u16(b + 80)), dmin = ggb_h2f(ld_u16(b + 82));
+        const uint32_t s0 = b[8 * n + 2 * s], s1 = b[8 * n + 2 * s + 1];
+        o.a0 = d * (float)(s0 & 0xf);
+        o.m0 = dmin * (float)(s0 >> 4);
+        o.a1 = d * (float)(s1 & 0xf);
+        o.m1 = dmin * (float)(s1 >> 4);
+#pragma unroll
+        for (int i = 0; i < 8; i++) o.w[i] = (ld_u32_a4(b + 16 + 32 * n + 4 * i) >> (2 * s)) & 0x03030303u;
+    } else if constexpr (TYPE == T_Q3_K) {
+        const uint8_t *b = seg + (g >> 3) * BS;
+        const int j = g & 7, n = j >> 2, jj = j & 3;
+        const float d = ggb_h2f(ld_u16(b + 108));
+        o.a0 = d * (float)q3k_scale(b + 96, 8 * n + 2 * jj);
+        o.a1 = d * (float)q3k_scale(b + 96, 8 * n + 2 * jj + 1);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t lo = (ld_u32_a2(b + 32 + 32 * n + 4 * i) >> (2 * jj)) & 0x03030303u;
+            const uint32_t hb = (ld_u32_a2(b + 4 * i) >> (4 * n + jj)) & 0x01010101u;
+            o.w[i] = lo | (hb << 2);                         // raw = value + 4
+        }
+    } else if constexpr (TYPE == T_Q4_K) {
+        const uint8_t *b = seg + (g >> 3) * BS;
+        const int j = g & 7, il = j >> 1, hi = j & 1;
+        int sc, mn;
+        k4_scale_min(j, b + 4, sc, mn);
+        o.a0 = o.a1 = ggb_h2f(ld_u16(b)) * (float)sc;
+        o.m0 = o.m1 = ggb_h2f(ld_u16(b + 2)) * (float)mn;
+#pragma unroll
+        for (int i = 0; i < 8; i++) o.w[i] = (ld_u32_a4(b + 16 + 32 * il + 4 * i) >> (4 * hi)) & 0x0f0f0f0fu;
+    } else if constexpr (TYPE == T_Q5_K) {
+        const uint8_t *b = seg + (g >> 3) * BS;
+        const int j = g & 7, il = j >> 1, hi = j & 1;
+        int sc, mn;
+        k4_scale_min(j, b + 4, sc, mn);
+        o.a0 = o.a1 = ggb_h2f(ld_u16(b)) * (float)sc;
+        o.m0 = o.m1 = ggb_h2f(ld_u16(b + 2)) * (float)mn;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t lo = (ld_u32_a4(b + 48 + 32 * il + 4 * i) >> (4 * hi)) & 0x0f0f0f0fu;
+            const uint32_t hb = (ld_u32_a4(b + 16 + 4 * i) >> j) & 0x01010101u;
+            o.w[i] = lo | (hb << 4);
+        }
+    } else {   // T_Q6_K
+        const uint8_t *b = seg + (g >> 3) * BS;
+        const int j = g & 7, ip = j >> 2, r = j & 3;
+        const float d = ggb_h2f(ld_u16(b + 208));
+        o.a0 = d * (float)(int)(int8_t)b[192 + 8 * ip + 2 * r];
+        o.a1 = d * (float)(int)(int8_t)b[192 + 8 * ip + 2 * r + 1];
+        const uint8_t *ql = b + 64 * ip + 32 * (r & 1);
+        const uint8_t *qh = b + 128 + 32 * ip;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t lo = (ld_u32_a2(ql + 4 * i) >> (4 * (r >> 1))) & 0x0f0f0f0fu;
+            const uint32_t hb = (ld_u32_a2(qh + 4 * i) >> (2 * r)) & 0x03030303u;
+            o.w[i] = lo | (hb << 4);                         // raw = value + 32
+        }
+    }
+}
+
+// fp32 contribution of one (row, batch, group): the reference's per-type algebra
+// (vecdotq.cuh:45-65 q4_0, :69-91 q4_1, :93-125 q5_0, :130-162 q5_1, :166-178 q8_0,
+//  :203-231 q2_K, :235-268 q3_K, :272-327 q4_K/q5_K, :331-349 q6_K).
+template <int TYPE>
+__device__ __forceinline__ float combine(const GroupW &g, int dot0, int dot1, float d8, uint32_t aux) {
+    if constexpr (TYPE == T_Q4_0 || TYPE == T_Q5_0) {
+        const float s8 = __uint_as_float(aux);
+        const float off = (TYPE == T_Q4_0) ? 8.0f : 16.0f;
+        return g.a0 * ((float)(dot0 + dot1) * d8 - off * s8);
+    } else if constexpr (TYPE == T_Q4_1 || TYPE == T_Q5_1) {
+        const float s8 = __uint_as_float(aux);
+        const float d4d8 = __half2float(__float2half_rn(g.a0 * d8));      // __hmul2(dm, ds8) in half
+        const float m4s8 = __half2float(__float2half_rn(g.m0 * s8));
+        return (float)(dot0 + dot1) * d4d8 + m4s8;
+    } else if constexpr (TYPE == T_Q8_0) {
+        return (g.a0 * d8) * (float)(dot0 + dot1);
+    } else {
+        const int sq0 = (int)(int16_t)(aux & 0xffffu), sq1 = (int)(int16_t)(aux >> 16);
+        if constexpr (TYPE == T_Q2_K) {
+            return d8 * (g.a0 * (float)dot0 + g.a1 * (float)dot1) - d8 * (g.m0 * (float)sq0 + g.m1 * (float)sq1);
+        } else if constexpr (TYPE == T_Q3_K) {
+            return d8 * (g.a0 * (float)(dot0 - 4 * sq0) + g.a1 * (float)(dot1 - 4 * sq1));
+        } else if constexpr (TYPE == T_Q6_K) {
+            return d8 * (g.a0 * (float)(dot0 - 32 * sq0) + g.a1 * (float)(dot1 - 32 * sq1));
+        } else {   // Q4_K, Q5_K
+            return d8 * (g.a0 * (float)(dot0 + dot1)) - d8 * (g.m0 * (float)(sq0 + sq1));
+        }
+    }
+}
+
+// ---------------------------------------------------------------- the kernel
+template <int TYPE, int B, typename T>
+__global__ void __launch_bounds__(kThreads, 1)
+mmvq_kernel(const Params p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    int8_t *act_q = reinterpret_cast<int8_t *>(smem);                          // [B][K]
+    float2 *act_s = reinterpret_cast<float2 *>(smem + p.off_scales);           // [B][K/32] {d8, aux}
+    uint8_t *stages = smem + p.off_stages;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + p.off_bars);
+    uint64_t *empty = full + kMaxStages;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int K = p.K, ngroups_row = K >> 5;
+    const int stage_bytes = kStageRows * p.seg_stride;
+
+    // this CTA's contiguous row range (byte-balanced: rows differ by at most one across CTAs)
+    const int64_t r_begin = p.N * (int64_t)blockIdx.x / gridDim.x;
+    const int64_t r_end = p.N * (int64_t)(blockIdx.x + 1) / gridDim.x;
+    const int nrows = (int)(r_end - r_begin);
+    const int nrgroups = (nrows + kStageRows - 1) / kStageRows;
+
+    if (tid == 0) {
+        for (int s = 0; s < p.nstages; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kConsumerWarps);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == kConsumerWarps) {
+        // ===================== producer warp: stream (row group, chunk) stages =====================
+        const uint64_t pol = l2_policy_evict_first();
+        int it = 0;
+        for (int rg = 0; rg < nrgroups; rg++) {
+            const int nvalid = min(kStageRows, nrows - rg * kStageRows);
+            const uint8_t *wrow = p.W + (r_begin + (int64_t)rg * kStageRows) * p.row_bytes;
+            for (int c = 0; c < p.nchunks; c++, it++) {
+                const int s = it % p.nstages;
+                const uint32_t ph = (uint32_t)(it / p.nstages) & 1u;
+                mbar_wait(&empty[s], ph ^ 1u);
+                const int seg_bytes = min(p.chunk_bytes, p.row_bytes - c * p.chunk_bytes);
+                uint8_t *dst = stages + s * stage_bytes;
+                const uint8_t *src = wrow + (int64_t)c * p.chunk_bytes;
+                if (p.fast) {
+                    if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)(nvalid * seg_bytes));
+                    __syncwarp();
+                    if (lane < nvalid)
+                        bulk_g2s_hint(dst + lane * p.seg_stride, src + (int64_t)lane * p.row_bytes, (uint32_t)seg_bytes,
+                                      &full[s], pol);
+                } else {
+                    // rows that are not 16-byte aligned (K not a multiple of 256 for some types): 2-byte copies
+                    for (int r = 0; r < nvalid; r++) {
+                        const uint16_t *s16 = reinterpret_cast<const uint16_t *>(src + (int64_t)r * p.row_bytes);
+                        uint16_t *d16 = reinterpret_cast<uint16_t *>(dst + r * p.seg_stride);
+                        for (int i = lane; i < seg_bytes / 2; i += 32) d16[i] = s16[i];
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full[s]);
+                }
+            }
+        }
+        return;
+    }
+
+    // ===================== consumers: quantize the activations to q8_1 in shared memory =====================
+    {
+        const T *X = static_cast<const T *>(p.X);
+        const int t4 = lane & 3;
+        const int total = B * ngroups_row;                       // groups; 4 lanes each
+        for (int base = 0; base < total; base += (kConsumerWarps * 32) / 4) {
+            const int gi = base + (tid >> 2);
+            const bool live = gi < total;
+            const int b = live ? gi / ngroups_row : 0;
+            const int g = live ? gi - b * ngroups_row : 0;
+            float v[8];
+            if (live) {
+                load8_f32<T>(X + (int64_t)b * K + g * 32 + t4 * 8, p.x_vec != 0, v);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; i++) v[i] = 0.0f;
+            }
+            const Q8Group q = q8_1_quantize_group<VqTraits<TYPE>::NEED_S8>(v);
+            uint32_t aux = 0;
+            if constexpr (VqTraits<TYPE>::NEED_SQ) {
+                int mine = __dp4a((int)q.q_lo, 0x01010101, __dp4a((int)q.q_hi, 0x01010101, 0));
+                mine += __shfl_xor_sync(0xffffffffu, mine, 1);                 // 16-value half sums
+                const int other = __shfl_xor_sync(0xffffffffu, mine, 2);
+                aux = ((uint32_t)mine & 0xffffu) | ((uint32_t)other << 16);   // valid on t4 == 0
+            } else if constexpr (VqTraits<TYPE>::NEED_S8) {
+                aux = __float_as_uint(__half2float(__float2half_rn(q.sum)));
+            }
+            if (live) {
+                *reinterpret_cast<uint2 *>(act_q + (int64_t)b * K + g * 32 + t4 * 8) = make_uint2(q.q_lo, q.q_hi);
+                if (t4 == 0)
+                    act_s[b * ngroups_row + g] = make_float2(__half2float(__float2half_rn(q.d)), __uint_as_float(aux));
+            }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory");
+    }
+
+    // ===================== consumers: stream stages, two rows per warp =====================
+    T *Y = static_cast<T *>(p.Y);
+    int it = 0;
+    for (int rg = 0; rg < nrgroups; rg++) {
+        float acc[kRowsPerWarp][B];
+#pragma unroll
+        for (int r = 0; r < kRowsPerWarp; r++)
+#pragma unroll
+            for (int b = 0; b < B; b++) acc[r][b] = 0.0f;
+
+        for (int c = 0; c < p.nchunks; c++, it++) {
+            const int s = it % p.nstages;
+            const uint32_t ph = (uint32_t)(it / p.nstages) & 1u;
+            mbar_wait(&full[s], ph);
+            const uint8_t *seg0 = stages + s * stage_bytes + (warp * kRowsPerWarp) * p.seg_stride;
+            const uint8_t *seg1 = seg0 + p.seg_stride;
+            const int ng = min(kChunkGroups, ngroups_row - c * kChunkGroups);
+            for (int g = lane; g < ng; g += 32) {
+                GroupW w0, w1;
+                load_group<TYPE>(seg0, g, w0);
+                load_group<TYPE>(seg1, g, w1);
+                const int gk = c * kChunkGroups + g;
+#pragma unroll
+                for (int b = 0; b < B; b++) {
+                    const uint4 ua = *reinterpret_cast<const uint4 *>(act_q + (int64_t)b * K + gk * 32);
+                    const uint4 ub = *reinterpret_cast<const uint4 *>(act_q + (int64_t)b * K + gk * 32 + 16);
+                    const float2 sc = act_s[b * ngroups_row + gk];
+                    const uint32_t aux = __float_as_uint(sc.y);
+                    int d00 = __dp4a((int)w0.w[0], (int)ua.x, 0), d01 = __dp4a((int)w0.w[4], (int)ub.x, 0);
+                    int d10 = __dp4a((int)w1.w[0], (int)ua.x, 0), d11 = __dp4a((int)w1.w[4], (int)ub.x, 0);
+                    d00 = __dp4a((int)w0.w[1], (int)ua.y, d00); d01 = __dp4a((int)w0.w[5], (int)ub.y, d01);
+                    d10 = __dp4a((int)w1.w[1], (int)ua.y, d10); d11 = __dp4a((int)w1.w[5], (int)ub.y, d11);
+                    d00 = __dp4a((int)w0.w[2], (int)ua.z, d00); d01 = __dp4a((int)w0.w[6], (int)ub.z, d01);
+                    d10 = __dp4a((int)w1.w[2], (int)ua.z, d10); d11 = __dp4a((int)w1.w[6], (int)ub.z, d11);
+                    d00 = __dp4a((int)w0.w[3], (int)ua.w, d00); d01 = __dp4a((int)w0.w[7], (int)ub.w, d01);
+                    d10 = __dp4a((int)w1.w[3], (int)ua.w, d10); d11 = __dp4a((int)w1.w[7], (int)ub.w, d11);
+                    acc[0][b] += combine<TYPE>(w0, d00, d01, sc.x, aux);
+                    acc[1][b] += combine<TYPE>(w1, d10, d11, sc.x, aux);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+
+        // warp-shuffle reduction, lane 0 stores (rows past the CTA's range computed on stale bytes: dropped)
+#pragma unroll
+        for (int r = 0; r < kRowsPerWarp; r++) {
+            const int lr = rg * kStageRows + warp * kRowsPerWarp + r;
+#pragma unroll
+            for (int b = 0; b < B; b++) {
+                float v = acc[r][b];
+#pragma unroll
+                for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+                if (lane == 0 && lr < nrows) Y[(int64_t)b * p.N + r_begin + lr] = from_f32<T>(v);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- host side
+template <int TYPE, int B, typename T>
+int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, cudaStream_t stream) {
+    constexpr int QK = BlockTraits<TYPE>::QK, BS = BlockTraits<TYPE>::BS;
+    const DeviceInfo &di = ggb_device_info();
+    Params p;
+    p.W = static_cast<const uint8_t *>(W);
+    p.X = X;
+    p.Y = Y;
+    p.N = N;
+    p.K = (int)K;
+    p.row_bytes = (int)(K / QK * BS);
+    p.chunk_bytes = kChunkElems / QK * BS;
+    p.nchunks = (int)((K + kChunkElems - 1) / kChunkElems);
+    const int seg = (int)(K < kChunkElems ? p.row_bytes : p.chunk_bytes);
+    p.seg_stride = (seg + 15) & ~15;
+    p.fast = ((reinterpret_cast<uintptr_t>(W) & 15) == 0) && (p.row_bytes % 16 == 0);
+    p.x_vec = (reinterpret_cast<uintptr_t>(X) & 15) == 0;
+    const int act_q = (int)(B * K);
+    p.off_scales = (act_q + 15) & ~15;
+    p.off_stages = (p.off_scales + (int)(B * (K / 32) * 8) + 127) & ~127;
+    const int stage_bytes = kStageRows * p.seg_stride;
+    const int bar_bytes = 2 * kMaxStages * 8;
+    const int avail = di.max_smem_optin - p.off_stages - bar_bytes - 128;
+    int nst = avail / stage_bytes;
+    if (nst < 2) return 1;                       // activations do not fit beside a 2-stage ring: caller splits B
+    if (nst > kMaxStages) nst = kMaxStages;
+    p.nstages = nst;
+    p.off_bars = (p.off_stages + nst * stage_bytes + 127) & ~127;
+    const int smem = p.off_bars + bar_bytes;
+
+    static bool attr_set[64] = {};               // per instantiation and device; idempotent, so a race is harmless
+    if (!attr_set[di.dev]) {
+        GGB_CUDA_TRY(cudaFuncSetAttribute(mmvq_kernel<TYPE, B, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          di.max_smem_optin));
+        attr_set[di.dev] = true;
+    }
+    const int grid = (int)(N < di.sm_count ? N : di.sm_count);
+    mmvq_kernel<TYPE, B, T><<<grid, kThreads, smem, stream>>>(p);
+    GGB_CUDA_TRY(cudaGetLastError());
+    return GGB_OK;
+}
+
+template <int TYPE, typename T>
+int dispatch_batch(const void *W, const void *X, void *Y, int64_t B, int64_t K, int64_t N, cudaStream_t stream) {
+    int rc;
+    switch (B) {
+        case 1: rc = launch<TYPE, 1, T>(W, X, Y, K, N, stream); break;
+        case 2: rc = launch<TYPE, 2, T>(W, X, Y, K, N, stream); break;
+        case 3: rc = launch<TYPE, 3, T>(W, X, Y, K, N, stream); break;
+        case 4: rc = launch<TYPE, 4, T>(W, X, Y, K, N, stream); break;
+        case 5: rc = launch<TYPE, 5, T>(W, X, Y, K, N, stream); break;
+        case 6: rc = launch<TYPE, 6, T>(W, X, Y, K, N, stream); break;
+        case 7: rc = launch<TYPE, 7, T>(W, X, Y, K, N, stream); break;
+        case 8: rc = launch<TYPE, 8, T>(W, X, Y, K, N, stream); break;
+        default:
+            ggb_set_error("ggb_mmvq: batch %lld outside 1..8", (long long)B);
+            return GGB_E_SHAPE;
+    }
+    if (rc != 1) return rc;
+    if (B == 1) {
+        ggb_set_error("ggb_mmvq: K=%lld is too large for one activation row in shared memory", (long long)K);
+        return GGB_E_SHAPE;
+    }
+    // the B x K activation tile does not fit in shared memory: two launches over half the batch each
+    const int64_t b1 = B / 2;
+    rc = dispatch_batch<TYPE, T>(W, X, Y, b1, K, N, stream);
+    if (rc != GGB_OK) return rc;
+    return dispatch_batch<TYPE, T>(W, static_cast<const T *>(X) + b1 * K, static_cast<T *>(Y) + b1 * N, B - b1, K, N,
+                                   stream);
+}
+
+template <int TYPE>
+int dispatch_dtype(const void *W, const void *X, void *Y, int dt, int64_t B, int64_t K, int64_t N, cudaStream_t stream) {
+    switch (dt) {
+        case GGB_F32:  return dispatch_batch<TYPE, float>(W, X, Y, B, K, N, stream);
+        case GGB_F16:  return dispatch_batch<TYPE, __half>(W, X, Y, B, K, N, stream);
+        case GGB_BF16: return dispatch_batch<TYPE, __nv_bfloat16>(W, X, Y, B, K, N, stream);
+        default:
+            ggb_set_error("ggb_mmvq: unknown dtype %d", dt);
+            return GGB_E_DTYPE;
+    }
+}
+
+}  // namespace
+
 int64_t ggb_mmvq_workspace_bytes_impl(int, int64_t, int64_t, int64_t) { return 0; }
-int ggb_mmvq_impl(const void *, const void *, void *, int, int, int64_t, int64_t, int64_t, void *, int64_t, cudaStream_t) {
-    ggb_set_error("ggb_mmvq: not built"); return GGB_E_TYPE;
+
+int ggb_mmvq_impl(const void *W, const void *X, void *Y, int type, int xy_dtype, int64_t B, int64_t K, int64_t N,
+                  void *, int64_t, cudaStream_t stream) {
+    if (K > (1 << 24)) {
+        ggb_set_error("ggb_mmvq: K=%lld too large", (long long)K);
+        return GGB_E_SHAPE;
+    }
+    switch (type) {
+        case T_Q4_0: return dispatch_dtype<T_Q4_0>(W, X, Y, xy_dtype, B, K, N, stream);
+        case T_Q4_1: return dispatch_dtype<T_Q4_1>(W, X, Y, xy_dtype, B, K, N, stream);
+        case T_Q5_0: return dispatch_dtype<T_Q5_0>(W, X, Y, xy_dtype, B, K, N, stream);
+        case T_Q5_1: return dispatch_dtype<T_Q5_1>(W, X, Y, xy_dtype, B, K, N, stream);
+        case T_Q8_0: return dispatch_dtype<T_Q8_0>(W, X, Y, xy_dtype, B, K, N, stream);
+        case T_Q2_K: return dispatch_dtype<T_Q2_K>(W, X, Y, xy_dtype, B, K, N, stream);
+        case T_Q3_K: return dispatch_dtype<T_Q3_K>(W, X, Y, xy_dtype, B, K, N, stream);
+        case T_Q4_K: return dispatch_dtype<T_Q4_K>(W, X, Y, xy_dtype, B, K, N, stream);
+        case T_Q5_K: return dispatch_dtype<T_Q5_K>(W, X, Y, xy_dtype, B, K, N, stream);
+        case T_Q6_K: return dispatch_dtype<T_Q6_K>(W, X, Y, xy_dtype, B, K, N, stream);
+        default:
+            ggb_set_error("ggb_mmvq: unsupported ggml type %d", type);
+            return GGB_E_TYPE;
+    }
 }

@@ -1,0 +1,114 @@
+"""GPU parity: ggml_mul_mat_vec_a8 (MMVQ, in-kernel q8_1 quantization) against the oracle's restatement
+of quantize_q8_1 + mul_mat_vec_q (ggml_kernel.cu:13-66, mmvq.cuh:2-38, vecdotq.cuh) and, like the
+reference's own test (test_cuda_kernels.py:61-81), against x @ dequant(W).T.
+
+Stated tolerance: the integer dot products are exact and the q8_1 quantization is bit-identical to
+the oracle's, so the only difference is fp32 summation order (the oracle accumulates in double):
+|y - oracle| <= 2e-5 * max|oracle| for fp32 outputs, plus one output rounding for fp16 (2^-10
+relative) / bf16 (2^-7 relative)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from util import MMVQ_ATOL, MMVQ_RTOL
+
+pytestmark = pytest.mark.gpu
+
+TYPES = oracle.ALL_TYPES
+IDS = [oracle.TYPE_NAMES[t] for t in TYPES]
+DTYPES = [torch.float32, torch.float16, torch.bfloat16]
+OUT_REL = {torch.float32: 0.0, torch.float16: 2.0 ** -10, torch.bfloat16: 2.0 ** -7}
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import ggml
+    return ggml
+
+
+def _check(ops, t, N, K, B, dtype, seed=0, dist="randn"):
+    w = oracle.random_weights(t, N, K, seed=seed + t)
+    g = torch.Generator().manual_seed(seed)
+    x = (torch.randn(B, K, generator=g) if dist == "randn" else torch.rand(B, K, generator=g)).to(dtype)
+    want = oracle.mmvq(w, t, x.float().numpy(), N)
+    got = ops.ggml_mul_mat_vec_a8(torch.from_numpy(w).cuda(), x.cuda(), t, N)
+    assert got.shape == (B, N) and got.dtype == dtype
+    got = got.float().cpu().numpy()
+    scale = float(np.abs(want).max()) + 1e-30
+    tol = 2e-5 * scale + OUT_REL[dtype] * np.abs(want) * 1.01
+    bad = np.abs(got - want) > tol
+    assert not bad.any(), (f"{oracle.TYPE_NAMES[t]} N={N} K={K} B={B} {dtype}: {bad.sum()} of {bad.size} off; "
+                           f"max err {np.abs(got - want).max():.3e} scale {scale:.3e}")
+    return w, x, got
+
+
+@pytest.mark.parametrize("B", [1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("t", TYPES, ids=IDS)
+def test_batches_fp32(ops, t, B):
+    _check(ops, t, 257, 2048, B, torch.float32)
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=["f32", "f16", "bf16"])
+@pytest.mark.parametrize("t", TYPES, ids=IDS)
+@pytest.mark.parametrize("shape", [(1, 256), (5, 512), (96, 1024), (300, 4096), (64, 6144), (33, 2304)])
+def test_shapes(ops, t, shape, dtype):
+    N, K = shape
+    _check(ops, t, N, K, 1, dtype, seed=N)
+    _check(ops, t, N, K, 3, dtype, seed=N + 1)
+
+
+@pytest.mark.parametrize("t", oracle.LEGACY_TYPES, ids=[oracle.TYPE_NAMES[t] for t in oracle.LEGACY_TYPES])
+def test_legacy_k_multiple_of_32(ops, t):
+    """legacy types only need K % 32 == 0 (rows then are not 16-byte aligned: the non-TMA path)."""
+    for N, K in [(17, 32), (40, 96), (9, 2080)]:
+        _check(ops, t, N, K, 2, torch.float32, seed=K)
+
+
+@pytest.mark.parametrize("hidden_size", [256, 1024])
+@pytest.mark.parametrize("dtype", [torch.half, torch.bfloat16, torch.float32], ids=["half", "bf16", "f32"])
+@pytest.mark.parametrize("t", TYPES, ids=IDS)
+def test_reference_style_mmvq(ops, t, dtype, hidden_size):
+    """test_cuda_kernels.py:61-81: x = torch.rand(1, H), expected = x @ dequant(W).T, atol 1, rtol 1e-1."""
+    torch.manual_seed(0)
+    x = torch.rand((1, hidden_size), dtype=dtype, device="cuda")
+    for rows in (hidden_size, 2 * hidden_size):
+        w = oracle.random_weights(t, rows, hidden_size, seed=rows)
+        weight = torch.tensor(oracle.dequantize(w, t, rows, hidden_size), device="cuda").to(dtype)
+        ref_output = x @ weight.T
+        qweight = torch.tensor(w, device="cuda")
+        output = ops.ggml_mul_mat_vec_a8(qweight, x, t, qweight.shape[0]).to(dtype)
+        torch.testing.assert_close(output, ref_output, atol=MMVQ_ATOL, rtol=MMVQ_RTOL)
+
+
+@pytest.mark.parametrize("t", [oracle.Q4_K, oracle.Q6_K], ids=["Q4_K", "Q6_K"])
+@pytest.mark.parametrize("shape", [(14336, 4096), (4096, 14336)])
+def test_config3_llama8b_shapes(ops, t, shape):
+    """BASELINE config 3: Llama-3-8B Q4_K_M decode GEMV shapes, batch 1 and 8, fp16."""
+    N, K = shape
+    for B in (1, 8):
+        _check(ops, t, N, K, B, torch.float16, seed=B)
+
+
+def test_linearity_property(ops):
+    """size-independent property at full size: rows of Y are independent, so a row-slice of W gives the
+    same values as the slice of the full result (bit-for-bit: same K order per row)."""
+    t, N, K = oracle.Q4_K, 14336, 4096
+    w = torch.from_numpy(oracle.random_weights(t, N, K, seed=5)).cuda()
+    x = torch.randn(4, K, dtype=torch.float16, device="cuda")
+    full = ops.ggml_mul_mat_vec_a8(w, x, t, N)
+    part = ops.ggml_mul_mat_vec_a8(w[1000:3000].contiguous(), x, t, 2000)
+    assert torch.equal(full[:, 1000:3000], part)
+    # and each batch row equals the batch-1 result for that row
+    one = ops.ggml_mul_mat_vec_a8(w, x[2:3].contiguous(), t, N)
+    assert torch.equal(full[2:3], one)
+
+
+def test_errors(ops):
+    w = torch.zeros(144 * 4, dtype=torch.uint8, device="cuda")
+    with pytest.raises(ValueError):
+        ops.ggml_mul_mat_vec_a8(w, torch.zeros(9, 256, device="cuda"), 12, 4)      # batch > 8
+    with pytest.raises(ValueError):
+        ops.ggml_mul_mat_vec_a8(w, torch.zeros(1, 512, device="cuda"), 12, 4)      # K mismatch
+    with pytest.raises(ValueError):
+        ops.ggml_mul_mat_vec_a8(w, torch.zeros(1, 256, device="cuda", dtype=torch.float64), 12, 4)
