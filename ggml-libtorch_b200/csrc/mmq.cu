@@ -1,6 +1,457 @@
-// placeholder replaced by the real kernel
-#include "ggb_common.cuh"
-int64_t ggb_mmq_workspace_bytes_impl(int, int64_t, int64_t, int64_t) { return 0; }
-int ggb_mmq_impl(const void *, const void *, void *, int, int, int64_t, int64_t, int64_t, int64_t, void *, int64_t, cudaStream_t) {
-    ggb_set_error("ggb_mmq: not built"); return GGB_E_TYPE;
+// mmq.cu -- quantized GEMM for prefill (MMQ) on sm_100a tensor cores: tcgen05.mma + TMEM + TMA bulk copies.
+//
+// Replaces ggml_mul_mat_a8 = quantize_mmq_q8_1_cuda + mul_mat_q (hf-kernels/ggml-kernels/ggml/mmq.cu:109-255,
+// ggml/mmq.cuh:1917-2031, tile picker kernel_instances/mmq_kernel.cuh:11-87).  The reference unpacks
+// weights to int32 lanes in shared memory and issues Ampere mma.sync s8 tiles of at most 64 x 128 with a
+// float rescale after every K=32 step on CUDA cores (mmq.cuh:1351-1361); Q2_K/Q3_K never touch tensor cores.
+//
+// Design (DESIGN.md "MMQ"): ggml's formats carry a float scale per 32 K-values on BOTH operands, so an
+// integer accumulator has to be drained and rescaled on CUDA cores every 32-deep step -- on tcgen05 that
+// drain costs ~8x the MMA itself.  Instead both operands are brought to fp16 with their scales applied
+// and the whole K extent accumulates in fp32 inside TMEM:
+//     A[i,k] = fp16( dequantize(W)[i,k] )        -- bit-identical to ggml_dequantize(..., fp16)
+//     B[j,k] = fp16( d8[j,k/32] * q8[j,k] )      -- the q8_1 quantization of X (bit-identical d8/q8)
+//     Y[j,i] = sum_k A[i,k] * B[j,k]             -- tcgen05.mma.kind::f16, fp32 accumulate in TMEM
+// Two launches: (1) quantize X to q8_1 and write the fp16 B operand as a pre-swizzled tile image into the
+// workspace; (2) the persistent warp-specialised GEMM:
+//     warp 0      producer: cp.async.bulk of raw GGUF row segments (128 rows x 256 columns per raw stage)
+//                 and of B tiles (one contiguous, pre-swizzled BN x 64 image per stage), mbarrier tx-count
+//     warps 6-13  unpack: raw bytes -> fp16 A tile in the 128-byte-swizzle K-major layout UMMA reads
+//     warp 1      one elected thread issues tcgen05.mma (M=128 weight rows, N=BN tokens, K=16) x4 per
+//                 stage and tcgen05.commit's the stage / the accumulator
+//     warps 2-5   epilogue: tcgen05.ld the fp32 accumulator (double-buffered in the 512 TMEM columns, so
+//                 it overlaps the next tile's MMAs), convert, store Y
+// Roofline: tensor pipe (dense fp16 -> fp32 accumulate); ops = 2*M*N*K.
+#include "q8_1.cuh"
+#include "unpack.cuh"
+
+bool ggb_mmq_need_sum(int type);     // quantize_q8_1.cu
+
+namespace {
+
+constexpr int BM = 128;              // weight rows per tile (UMMA M)
+constexpr int KSTEP = 64;            // K elements per A/B stage: 128 B of fp16 = one SWIZZLE_128B row
+constexpr int RAWK = 256;            // K elements per raw-weight stage
+constexpr int NSTAGE = 3;
+constexpr int NRAW = 2;
+constexpr int kUnpackWarps = 8;
+constexpr int kFirstEpiWarp = 2, kFirstUnpackWarp = 6;
+constexpr int kThreads = (kFirstUnpackWarp + kUnpackWarps) * 32;     // 448
+constexpr int A_STAGE_BYTES = BM * 128;
+
+struct Params {
+    const uint8_t *W;
+    const uint8_t *Ximg;     // pre-swizzled fp16 B operand image (workspace)
+    void *Y;
+    int64_t N, M, ldy;
+    int K;
+    int row_bytes;           // bytes per weight row
+    int nsb;                 // raw stages per tile = ceil(K / 256)
+    int Mp;                  // tokens padded to a multiple of BN
+    int n_row_blocks, n_tok_tiles;
+    int raw_slot;            // bytes per row in a raw stage
+    int w_fast;              // W 16-byte aligned and total bytes % 16 == 0: bulk copies
+    int w_lo;                // low 4 bits of W (0 in the fast path)
+    int off_b, off_raw, off_bar;
+};
+
+// ---------------------------------------------------------------- tcgen05 / descriptor helpers
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    // K-major, SWIZZLE_128B canonical layout: rows of 128 B, 8-row atoms 1024 B apart (SBO), LBO unused (=1),
+    // descriptor version 1 (sm_100), layout_type 2 = SWIZZLE_128B.   (cute/arch/mma_sm100_desc.hpp)
+    return (uint64_t)((saddr & 0x3ffffu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s_plain(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ---------------------------------------------------------------- launch 1: q8_1 quantize -> fp16 B image
+// Image layout: [K/64 stages][Mp/8 token atoms][8 rows x 128 B, 16-byte chunks XOR-swizzled by row&7] --
+// exactly the bytes a SWIZZLE_128B TMA load would put in shared memory, so a BN x 64 B tile is ONE
+// contiguous bulk copy.  d8 is rounded to fp16 for the need_sum weight types (it is stored in a half2
+// there, mmq.cu:149-153) and kept in fp32 otherwise.
+template <typename T, bool D_HALF>
+__global__ void __launch_bounds__(256)
+quantize_b_image_kernel(const T *__restrict__ x, uint8_t *__restrict__ img, int64_t M, int K, int Kp, int Mp, bool vec_ok) {
+    const int groups_per_row = Kp / 32;
+    const int64_t gid = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 2;
+    const int t = threadIdx.x & 3;
+    const int64_t total = M * groups_per_row;
+    const bool live = gid < total;
+    const int64_t row = live ? gid / groups_per_row : 0;
+    const int g = live ? (int)(gid % groups_per_row) : 0;
+    const int k0 = g * 32 + t * 8;
+    float v[8];
+    if (live && k0 + 8 <= K) {
+        load8_f32<T>(x + row * K + k0, vec_ok, v);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = (live && k0 + i < K) ? to_f32<T>(x[row * K + k0 + i]) : 0.0f;
+    }
+    const Q8Group r = q8_1_quantize_group<false>(v);
+    if (!live) return;
+    const float d = D_HALF ? __half2float(__float2half_rn(r.d)) : r.d;
+    float y[8];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        y[i] = __fmul_rn(d, (float)(int)(int8_t)(r.q_lo >> (8 * i)));
+        y[i + 4] = __fmul_rn(d, (float)(int)(int8_t)(r.q_hi >> (8 * i)));
+    }
+    const int ks = k0 >> 6, c = (k0 & 63) >> 3;
+    const int64_t atom = row >> 3;
+    const int r8 = (int)(row & 7);
+    uint8_t *dst = img + ((int64_t)ks * (Mp >> 3) + atom) * 1024 + r8 * 128 + ((c ^ r8) << 4);
+    store8(reinterpret_cast<__half *>(dst), y);
+}
+
+// ---------------------------------------------------------------- launch 2: the GEMM
+template <int TYPE, int BN, typename T>
+__global__ void __launch_bounds__(kThreads, 1)
+mmq_kernel(const Params p) {
+    constexpr int QK = BlockTraits<TYPE>::QK, BS = BlockTraits<TYPE>::BS;
+    constexpr int SB_BYTES = RAWK / QK * BS;                  // raw bytes per row per raw stage
+    constexpr int B_STAGE_BYTES = BN * 128;
+    constexpr int ACC_COLS = (BN < 32) ? 32 : BN;             // TMEM columns per accumulator buffer
+    constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);   // f16 x f16 -> f32, K-major
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // SWIZZLE_128B operands need 1024-byte aligned tiles; the launch reserves the slack
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *sA = smem;
+    uint8_t *sB = smem + p.off_b;
+    uint8_t *sRaw = smem + p.off_raw;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + p.off_bar);
+    uint64_t *raw_full = bars, *raw_empty = bars + NRAW;
+    uint64_t *a_full = bars + 2 * NRAW, *b_full = a_full + NSTAGE, *ab_empty = b_full + NSTAGE;
+    uint64_t *acc_full = ab_empty + NSTAGE, *acc_empty = acc_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ntiles = p.n_row_blocks * p.n_tok_tiles;
+    const int ksteps_total = p.nsb * (RAWK / KSTEP);
+
+    if (tid == 0) {
+        for (int s = 0; s < NRAW; s++) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], kUnpackWarps); }
+        for (int s = 0; s < NSTAGE; s++) { mbar_init(&a_full[s], kUnpackWarps); mbar_init(&b_full[s], 1); mbar_init(&ab_empty[s], 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+        fence_mbar_init();
+    }
+    if (warp == 1) {   // TMEM: all 512 columns (two accumulator buffers); one CTA per SM so no contention
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ============================ producer ============================
+        int it = 0, rit = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int rb = tile % p.n_row_blocks, tt = tile / p.n_row_blocks;
+            const int64_t row0 = (int64_t)rb * BM;
+            for (int sb = 0; sb < p.nsb; sb++, rit++) {
+                const int rs = rit % NRAW;
+                mbar_wait(&raw_empty[rs], ((uint32_t)(rit / NRAW) & 1u) ^ 1u);
+                uint8_t *dst = sRaw + rs * (BM * p.raw_slot);
+                const int seg_len = min(SB_BYTES, p.row_bytes - sb * SB_BYTES);
+                if (p.w_fast) {
+                    uint32_t mybytes = 0;
+                    int64_t a0[4];
+                    uint32_t len[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int r = lane + 32 * i;
+                        const int64_t off = (row0 + r) * p.row_bytes + (int64_t)sb * SB_BYTES;
+                        a0[i] = off & ~(int64_t)15;
+                        len[i] = (row0 + r < p.N) ? (uint32_t)((((int)(off & 15) + seg_len) + 15) & ~15) : 0u;
+                        mybytes += len[i];
+                    }
+#pragma unroll
+                    for (int m = 16; m > 0; m >>= 1) mybytes += __shfl_xor_sync(0xffffffffu, mybytes, m);
+                    if (lane == 0) mbar_expect_tx(&raw_full[rs], mybytes);
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        if (len[i]) bulk_g2s_plain(dst + (lane + 32 * i) * p.raw_slot, p.W + a0[i], len[i], &raw_full[rs]);
+                } else {
+                    for (int r = 0; r < BM; r++) {
+                        if (row0 + r >= p.N) break;
+                        const uint16_t *s16 = reinterpret_cast<const uint16_t *>(p.W + (row0 + r) * p.row_bytes + (int64_t)sb * SB_BYTES);
+                        uint16_t *d16 = reinterpret_cast<uint16_t *>(dst + r * p.raw_slot);
+                        for (int i = lane; i < seg_len / 2; i += 32) d16[i] = s16[i];
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&raw_full[rs]);
+                }
+                for (int q = 0; q < RAWK / KSTEP; q++, it++) {
+                    const int s = it % NSTAGE;
+                    mbar_wait(&ab_empty[s], ((uint32_t)(it / NSTAGE) & 1u) ^ 1u);
+                    if (lane == 0) {
+                        const int ks = sb * (RAWK / KSTEP) + q;
+                        const uint8_t *src = p.Ximg + ((int64_t)ks * (p.Mp >> 3) + (int64_t)tt * (BN >> 3)) * 1024;
+                        mbar_expect_tx(&b_full[s], B_STAGE_BYTES);
+                        bulk_g2s_plain(sB + s * B_STAGE_BYTES, src, B_STAGE_BYTES, &b_full[s]);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ============================ MMA issuer (one thread) ============================
+        if (lane == 0) {
+            int it = 0, tcount = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
+                const int ab = tcount & 1;
+                mbar_wait(&acc_empty[ab], ((uint32_t)(tcount >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(ab * ACC_COLS);
+                for (int ks = 0; ks < ksteps_total; ks++, it++) {
+                    const int s = it % NSTAGE;
+                    const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u;
+                    mbar_wait(&a_full[s], ph);
+                    mbar_wait(&b_full[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(sA + s * A_STAGE_BYTES);
+                    const uint32_t b_addr = smem_u32(sB + s * B_STAGE_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < KSTEP / 16; kk++)
+                        umma_f16(d_tmem, umma_desc_sw128(a_addr + kk * 32), umma_desc_sw128(b_addr + kk * 32), IDESC,
+                                 (ks > 0 || kk > 0) ? 1u : 0u);
+                    umma_commit(&ab_empty[s]);                 // frees the A/B stage when these MMAs retire
+                }
+                umma_commit(&acc_full[ab]);                    // accumulator complete
+            }
+        }
+        __syncwarp();
+    } else if (warp < kFirstUnpackWarp) {
+        // ============================ epilogue (4 warps = 4 TMEM lane quadrants) ============================
+        const int quad = warp & 3;
+        T *Y = static_cast<T *>(p.Y);
+        int tcount = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
+            const int rb = tile % p.n_row_blocks, tt = tile / p.n_row_blocks;
+            const int ab = tcount & 1;
+            mbar_wait(&acc_full[ab], (uint32_t)(tcount >> 1) & 1u);
+            tc_fence_after();
+            const int64_t wrow = (int64_t)rb * BM + quad * 32 + lane;
+            const int64_t tok0 = (int64_t)tt * BN;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * ACC_COLS);
+            constexpr int NCH = (BN + 31) / 32;
+#pragma unroll 1
+            for (int ch = 0; ch < NCH; ch++) {
+                uint32_t v[32];
+                tmem_ld32(taddr + ch * 32, v);
+                tmem_ld_wait();
+                if (wrow < p.N) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const int64_t tok = tok0 + ch * 32 + j;
+                        if (ch * 32 + j < BN && tok < p.M) Y[tok * p.ldy + wrow] = from_f32<T>(__uint_as_float(v[j]));
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[ab]);
+        }
+    } else {
+        // ============================ unpack warps: raw GGUF bytes -> fp16 swizzled A tile ============================
+        const int u = tid - kFirstUnpackWarp * 32;             // 0..255
+        int it = 0, rit = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int rb = tile % p.n_row_blocks;
+            const int64_t row0 = (int64_t)rb * BM;
+            for (int sb = 0; sb < p.nsb; sb++, rit++) {
+                const int rs = rit % NRAW;
+                mbar_wait(&raw_full[rs], (uint32_t)(rit / NRAW) & 1u);
+                const uint8_t *raw = sRaw + rs * (BM * p.raw_slot);
+                for (int q = 0; q < RAWK / KSTEP; q++, it++) {
+                    const int s = it % NSTAGE;
+                    mbar_wait(&ab_empty[s], ((uint32_t)(it / NSTAGE) & 1u) ^ 1u);
+                    uint8_t *a_stage = sA + s * A_STAGE_BYTES;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int item = i * 256 + u;
+                        const int r = item >> 3, c = item & 7;
+                        const int e = q * KSTEP + c * 8;                       // element offset inside the raw stage
+                        float y[8];
+                        if (sb * RAWK + e < p.K) {
+                            const int slot_off = p.w_fast ? (int)(((row0 + r) * p.row_bytes + (int64_t)sb * SB_BYTES) & 15) : 0;
+                            const uint8_t *blk = raw + r * p.raw_slot + slot_off + (e / QK) * BS;
+                            Unpack8<TYPE>::run(blk, (e % QK) >> 3, y);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 8; k++) y[k] = 0.0f;
+                        }
+                        store8(reinterpret_cast<__half *>(a_stage + r * 128 + ((c ^ (r & 7)) << 4)), y);
+                    }
+                    fence_proxy_async();                       // generic-proxy stores -> visible to the UMMA (async proxy)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&a_full[s]);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&raw_empty[rs]);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------- host side
+int pick_bn(int64_t M) {
+    if (M > 128) return 256;
+    if (M > 64) return 128;
+    if (M > 32) return 64;
+    if (M > 16) return 32;
+    return 16;
+}
+int64_t padded_k(int64_t K) { return (K + RAWK - 1) / RAWK * RAWK; }
+int64_t padded_m(int64_t M) { const int bn = pick_bn(M); return (M + bn - 1) / bn * bn; }
+
+template <typename T>
+int launch_quantize(const void *X, int64_t M, int64_t K, uint8_t *img, bool d_half, cudaStream_t stream) {
+    const int64_t Kp = padded_k(K), Mp = padded_m(M);
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(X) % 16 == 0) && (K % 8 == 0);
+    const int64_t nthreads = M * (Kp / 32) * 4;
+    const int64_t nblk = (nthreads + 255) / 256;
+    if (nblk > 0x7fffffffLL) {
+        ggb_set_error("ggb_mmq: activation matrix too large");
+        return GGB_E_SHAPE;
+    }
+    const T *x = static_cast<const T *>(X);
+    if (d_half) quantize_b_image_kernel<T, true><<<(unsigned)nblk, 256, 0, stream>>>(x, img, M, (int)K, (int)Kp, (int)Mp, vec_ok);
+    else        quantize_b_image_kernel<T, false><<<(unsigned)nblk, 256, 0, stream>>>(x, img, M, (int)K, (int)Kp, (int)Mp, vec_ok);
+    GGB_CUDA_TRY(cudaGetLastError());
+    return GGB_OK;
+}
+
+template <int TYPE, int BN, typename T>
+int launch_gemm(const void *W, const uint8_t *img, void *Y, int64_t M, int64_t K, int64_t N, int64_t ldy, cudaStream_t stream) {
+    constexpr int QK = BlockTraits<TYPE>::QK, BS = BlockTraits<TYPE>::BS;
+    constexpr int SB_BYTES = RAWK / QK * BS;
+    const DeviceInfo &di = ggb_device_info();
+    Params p;
+    p.W = static_cast<const uint8_t *>(W);
+    p.Ximg = img;
+    p.Y = Y;
+    p.N = N;
+    p.M = M;
+    p.ldy = ldy;
+    p.K = (int)K;
+    p.row_bytes = (int)(K / QK * BS);
+    p.nsb = (int)(padded_k(K) / RAWK);
+    p.Mp = (int)padded_m(M);
+    p.n_row_blocks = (int)((N + BM - 1) / BM);
+    p.n_tok_tiles = p.Mp / BN;
+    p.raw_slot = (SB_BYTES + 30 + 15) & ~15;
+    const int64_t total = N * (int64_t)p.row_bytes;
+    p.w_fast = ((reinterpret_cast<uintptr_t>(W) & 15) == 0) && (total % 16 == 0);
+    p.w_lo = (int)(reinterpret_cast<uintptr_t>(W) & 15);
+    p.off_b = NSTAGE * A_STAGE_BYTES;
+    p.off_raw = p.off_b + NSTAGE * BN * 128;
+    p.off_raw = (p.off_raw + 1023) & ~1023;
+    p.off_bar = (p.off_raw + NRAW * BM * p.raw_slot + 127) & ~127;
+    const int smem = p.off_bar + 256 + 1024;     // + slack so the kernel can align its base to 1024
+    if (smem > di.max_smem_optin) {
+        ggb_set_error("ggb_mmq: tile needs %d bytes of shared memory (limit %d)", smem, di.max_smem_optin);
+        return GGB_E_SHAPE;
+    }
+    static bool attr_set[64] = {};
+    if (!attr_set[di.dev]) {
+        GGB_CUDA_TRY(cudaFuncSetAttribute(mmq_kernel<TYPE, BN, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin));
+        attr_set[di.dev] = true;
+    }
+    const int64_t ntiles = (int64_t)p.n_row_blocks * p.n_tok_tiles;
+    const int grid = (int)(ntiles < di.sm_count ? ntiles : di.sm_count);
+    mmq_kernel<TYPE, BN, T><<<grid, kThreads, smem, stream>>>(p);
+    GGB_CUDA_TRY(cudaGetLastError());
+    return GGB_OK;
+}
+
+template <int TYPE, typename T>
+int run_typed(const void *W, const void *X, void *Y, int64_t M, int64_t K, int64_t N, int64_t ldy, uint8_t *img, cudaStream_t stream) {
+    int rc = launch_quantize<T>(X, M, K, img, ggb_mmq_need_sum(TYPE), stream);
+    if (rc != GGB_OK) return rc;
+    switch (pick_bn(M)) {
+        case 256: return launch_gemm<TYPE, 256, T>(W, img, Y, M, K, N, ldy, stream);
+        case 128: return launch_gemm<TYPE, 128, T>(W, img, Y, M, K, N, ldy, stream);
+        case 64:  return launch_gemm<TYPE, 64, T>(W, img, Y, M, K, N, ldy, stream);
+        case 32:  return launch_gemm<TYPE, 32, T>(W, img, Y, M, K, N, ldy, stream);
+        default:  return launch_gemm<TYPE, 16, T>(W, img, Y, M, K, N, ldy, stream);
+    }
+}
+
+template <int TYPE>
+int run_dtype(const void *W, const void *X, void *Y, int dt, int64_t M, int64_t K, int64_t N, int64_t ldy, uint8_t *img, cudaStream_t stream) {
+    switch (dt) {
+        case GGB_F32:  return run_typed<TYPE, float>(W, X, Y, M, K, N, ldy, img, stream);
+        case GGB_F16:  return run_typed<TYPE, __half>(W, X, Y, M, K, N, ldy, img, stream);
+        case GGB_BF16: return run_typed<TYPE, __nv_bfloat16>(W, X, Y, M, K, N, ldy, img, stream);
+        default:
+            ggb_set_error("ggb_mmq: unknown dtype %d", dt);
+            return GGB_E_DTYPE;
+    }
+}
+
+}  // namespace
+
+int64_t ggb_mmq_workspace_bytes_impl(int, int64_t M, int64_t K, int64_t) {
+    return padded_k(K) * padded_m(M) * 2;       // the fp16 B-operand image
+}
+
+int ggb_mmq_impl(const void *W, const void *X, void *Y, int type, int xy_dtype, int64_t M, int64_t K, int64_t N,
+                 int64_t ldy, void *ws, int64_t, cudaStream_t stream) {
+    if (K > (1 << 24) || M > (1LL << 30) || N > (1LL << 30)) {
+        ggb_set_error("ggb_mmq: shape too large");
+        return GGB_E_SHAPE;
+    }
+    uint8_t *img = static_cast<uint8_t *>(ws);
+    switch (type) {
+        case T_Q4_0: return run_dtype<T_Q4_0>(W, X, Y, xy_dtype, M, K, N, ldy, img, stream);
+        case T_Q4_1: return run_dtype<T_Q4_1>(W, X, Y, xy_dtype, M, K, N, ldy, img, stream);
+        case T_Q5_0: return run_dtype<T_Q5_0>(W, X, Y, xy_dtype, M, K, N, ldy, img, stream);
+        case T_Q5_1: return run_dtype<T_Q5_1>(W, X, Y, xy_dtype, M, K, N, ldy, img, stream);
+        case T_Q8_0: return run_dtype<T_Q8_0>(W, X, Y, xy_dtype, M, K, N, ldy, img, stream);
+        case T_Q2_K: return run_dtype<T_Q2_K>(W, X, Y, xy_dtype, M, K, N, ldy, img, stream);
+        case T_Q3_K: return run_dtype<T_Q3_K>(W, X, Y, xy_dtype, M, K, N, ldy, img, stream);
+        case T_Q4_K: return run_dtype<T_Q4_K>(W, X, Y, xy_dtype, M, K, N, ldy, img, stream);
+        case T_Q5_K: return run_dtype<T_Q5_K>(W, X, Y, xy_dtype, M, K, N, ldy, img, stream);
+        case T_Q6_K: return run_dtype<T_Q6_K>(W, X, Y, xy_dtype, M, K, N, ldy, img, stream);
+        default:
+            ggb_set_error("ggb_mmq: unsupported ggml type %d", type);
+            return GGB_E_TYPE;
+    }
 }

@@ -31,3 +31,19 @@ def bf16_bits_from_f32(x: np.ndarray) -> np.ndarray:
     r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16).astype(np.uint16)
     r[np.isnan(x)] = 0x7FFF
     return r
+
+
+def mmq_b_operand_fp16(x32: np.ndarray, need_sum: bool) -> np.ndarray:
+    """fp16(d8 * q8) per element, from the ORACLE's q8_1_mmq blocks: the B operand the MMQ kernel feeds
+    the tensor cores (d8 is fp16-rounded for need_sum weight types, fp32 otherwise; mmq.cu:149-153)."""
+    import oracle
+    M, K = x32.shape
+    blocks = oracle.quantize_q8_1_mmq(x32, need_sum)            # [Kp/128, M, 144]
+    nch = blocks.shape[0]
+    q = blocks[:, :, 16:].view(np.int8).astype(np.float32).reshape(nch, M, 4, 32)
+    if need_sum:
+        d = blocks[:, :, :16].copy().view(np.float16).reshape(nch, M, 4, 2)[..., 0].astype(np.float32)
+    else:
+        d = blocks[:, :, :16].copy().view(np.float32).reshape(nch, M, 4)
+    y = (d[..., None] * q).astype(np.float16)                    # one fp32 product, one RN to fp16
+    return y.transpose(1, 0, 2, 3).reshape(M, nch * 128)[:, :K]
