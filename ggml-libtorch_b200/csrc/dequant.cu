@@ -60,15 +60,31 @@ dequant_tile_kernel(const uint8_t *__restrict__ W, OutT *__restrict__ out, int64
         __syncthreads();
     }
 
+    // K-quants: decode every (d*sc, dmin*m) pair of the tile ONCE (one or two per thread) instead of once per
+    // 8-value item; the legacy types read their block header inline.
+    constexpr int NSUB = Unpack8<TYPE>::NSUB;
+    constexpr int NTAB = (NSUB > 1) ? TILE_BLOCKS * NSUB : 1;
+    __shared__ float2 sc_tab[NTAB];
+    if constexpr (NSUB > 1) {
+        for (int e = tid; e < nb * NSUB; e += kThreads) sc_tab[e] = Unpack8<TYPE>::sub_scale(tile + (e / NSUB) * BS, e % NSUB);
+        __syncthreads();
+    }
+
+    // item = 8 consecutive values.  Thread t always handles octet p = t % ITEMS_PER_BLOCK of blocks
+    // t / ITEMS_PER_BLOCK + k * BLK_STEP, so everything derived from p (shifts, byte offsets) is loop-invariant;
+    // consecutive threads write consecutive 16-byte chunks (a warp store covers 512 contiguous bytes).
     OutT *dst = out + b0 * QK;
-    const int nitems = nb * ITEMS_PER_BLOCK;
+    constexpr int BLK_STEP = kThreads / ITEMS_PER_BLOCK;
+    static_assert(kThreads % ITEMS_PER_BLOCK == 0 && TILE_BLOCKS % BLK_STEP == 0, "tile/thread geometry");
+    const int p = tid % ITEMS_PER_BLOCK, blk0 = tid / ITEMS_PER_BLOCK;
 #pragma unroll
-    for (int it = tid; it < TILE_BLOCKS * ITEMS_PER_BLOCK; it += kThreads) {
-        if (it < nitems) {
-            const int blk = it / ITEMS_PER_BLOCK, p = it % ITEMS_PER_BLOCK;
+    for (int k = 0; k < TILE_BLOCKS / BLK_STEP; k++) {
+        const int blk = blk0 + k * BLK_STEP;
+        if (blk < nb) {
             float y[8];
-            Unpack8<TYPE>::run(tile + blk * BS, p, y);
-            store8(dst + (int64_t)it * 8, y);
+            if constexpr (NSUB > 1) Unpack8<TYPE>::run_sc(tile + blk * BS, p, sc_tab[blk * NSUB + Unpack8<TYPE>::sub_of(p)], y);
+            else                    Unpack8<TYPE>::run(tile + blk * BS, p, y);
+            store8(dst + ((int64_t)blk * ITEMS_PER_BLOCK + p) * 8, y);
         }
     }
 }

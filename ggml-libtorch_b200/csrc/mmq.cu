@@ -22,8 +22,10 @@
 //     warps 2-5   epilogue: tcgen05.ld the fp32 accumulator (double-buffered in the 512 TMEM columns, so
 //                 it overlaps the next tile's MMAs), convert, store Y
 // Roofline: tensor pipe (dense fp16 -> fp32 accumulate); ops = 2*M*N*K.
+#include <cuda.h>          // CUtensorMap (types only: the encode entry point is fetched at run time)
+
 #include "q8_1.cuh"
-#include "unpack.cuh"
+#include "mmq_unpack.cuh"
 
 bool ggb_mmq_need_sum(int type);     // quantize_q8_1.cu
 
@@ -52,7 +54,7 @@ struct Params {
     int raw_slot;            // bytes per row in a raw stage
     int w_fast;              // W 16-byte aligned and total bytes % 16 == 0: bulk copies
     int w_lo;                // low 4 bits of W (0 in the fast path)
-    int off_b, off_raw, off_bar;
+    int off_b, off_raw, off_tab, off_bar;
 };
 
 // ---------------------------------------------------------------- tcgen05 / descriptor helpers
@@ -88,6 +90,13 @@ __device__ __forceinline__ void bulk_g2s_plain(void *smem_dst, const void *gsrc,
     asm volatile(
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
         ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// 2-D tiled TMA load (box = 128 rows x BOX_INNER bytes of raw GGUF data), completion on an mbarrier
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *tmap, int c0, int c1, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
 
 // ---------------------------------------------------------------- launch 1: q8_1 quantize -> fp16 B image
@@ -132,9 +141,12 @@ quantize_b_image_kernel(const T *__restrict__ x, uint8_t *__restrict__ img, int6
 // ---------------------------------------------------------------- launch 2: the GEMM
 template <int TYPE, int BN, typename T>
 __global__ void __launch_bounds__(kThreads, 1)
-mmq_kernel(const Params p) {
+mmq_kernel(const Params p, const __grid_constant__ CUtensorMap tmapW) {
     constexpr int QK = BlockTraits<TYPE>::QK, BS = BlockTraits<TYPE>::BS;
     constexpr int SB_BYTES = RAWK / QK * BS;                  // raw bytes per row per raw stage
+    // TMA box width in bytes (also the raw row slot).  The box must START on a 16-byte boundary, so for block sizes
+    // that are not multiples of 16 (Q2_K 84, Q3_K 110, Q6_K 210) it starts up to 14 bytes early.
+    constexpr int BOX_INNER = (SB_BYTES + ((SB_BYTES % 16) ? 14 : 0) + 15) & ~15;
     constexpr int B_STAGE_BYTES = BN * 128;
     constexpr int ACC_COLS = (BN < 32) ? 32 : BN;             // TMEM columns per accumulator buffer
     constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);   // f16 x f16 -> f32, K-major
@@ -145,6 +157,7 @@ mmq_kernel(const Params p) {
     uint8_t *sA = smem;
     uint8_t *sB = smem + p.off_b;
     uint8_t *sRaw = smem + p.off_raw;
+    uint32_t *sTab = reinterpret_cast<uint32_t *>(smem + p.off_tab);     // half2 (d*sc, -dmin*m) per sub-block, per raw stage
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + p.off_bar);
     uint64_t *raw_full = bars, *raw_empty = bars + NRAW;
     uint64_t *a_full = bars + 2 * NRAW, *b_full = a_full + NSTAGE, *ab_empty = b_full + NSTAGE;
@@ -182,24 +195,13 @@ mmq_kernel(const Params p) {
                 uint8_t *dst = sRaw + rs * (BM * p.raw_slot);
                 const int seg_len = min(SB_BYTES, p.row_bytes - sb * SB_BYTES);
                 if (p.w_fast) {
-                    uint32_t mybytes = 0;
-                    int64_t a0[4];
-                    uint32_t len[4];
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const int r = lane + 32 * i;
-                        const int64_t off = (row0 + r) * p.row_bytes + (int64_t)sb * SB_BYTES;
-                        a0[i] = off & ~(int64_t)15;
-                        len[i] = (row0 + r < p.N) ? (uint32_t)((((int)(off & 15) + seg_len) + 15) & ~15) : 0u;
-                        mybytes += len[i];
+                    // ONE tiled TMA load: 128 rows x BOX_INNER bytes starting at this raw stage's column; rows past
+                    // N and bytes past the row end are zero-filled by the TMA unit.
+                    if (lane == 0) {
+                        mbar_expect_tx(&raw_full[rs], (uint32_t)(BM * BOX_INNER));
+                        tma_load_2d(dst, &tmapW, ((sb * SB_BYTES) & ~15) / 2, (int)row0, &raw_full[rs]);
                     }
-#pragma unroll
-                    for (int m = 16; m > 0; m >>= 1) mybytes += __shfl_xor_sync(0xffffffffu, mybytes, m);
-                    if (lane == 0) mbar_expect_tx(&raw_full[rs], mybytes);
                     __syncwarp();
-#pragma unroll
-                    for (int i = 0; i < 4; i++)
-                        if (len[i]) bulk_g2s_plain(dst + (lane + 32 * i) * p.raw_slot, p.W + a0[i], len[i], &raw_full[rs]);
                 } else {
                     for (int r = 0; r < BM; r++) {
                         if (row0 + r >= p.N) break;
@@ -292,6 +294,16 @@ mmq_kernel(const Params p) {
                 const int rs = rit % NRAW;
                 mbar_wait(&raw_full[rs], (uint32_t)(rit / NRAW) & 1u);
                 const uint8_t *raw = sRaw + rs * (BM * p.raw_slot);
+                const int slot_off = p.w_fast ? ((sb * SB_BYTES) & 15) : 0;     // rows are 16-byte aligned in the TMA path
+                using HU = HalfUnpack<TYPE>;
+                uint32_t *tab = sTab + rs * (BM * HU::NSUB);
+                if constexpr (HU::HAS) {
+                    // decode every sub-block's (scale, min) pair of this raw stage once; the table is double-buffered
+                    // with the raw ring, so this one barrier per raw stage also orders its reuse
+                    for (int e = u; e < BM * HU::NSUB; e += kUnpackWarps * 32)
+                        tab[e] = HU::sub_scale(raw + (e / HU::NSUB) * p.raw_slot + slot_off, e % HU::NSUB);
+                    asm volatile("bar.sync 1, %0;" ::"n"(kUnpackWarps * 32) : "memory");
+                }
                 for (int q = 0; q < RAWK / KSTEP; q++, it++) {
                     const int s = it % NSTAGE;
                     mbar_wait(&ab_empty[s], ((uint32_t)(it / NSTAGE) & 1u) ^ 1u);
@@ -301,16 +313,21 @@ mmq_kernel(const Params p) {
                         const int item = i * 256 + u;
                         const int r = item >> 3, c = item & 7;
                         const int e = q * KSTEP + c * 8;                       // element offset inside the raw stage
-                        float y[8];
-                        if (sb * RAWK + e < p.K) {
-                            const int slot_off = p.w_fast ? (int)(((row0 + r) * p.row_bytes + (int64_t)sb * SB_BYTES) & 15) : 0;
-                            const uint8_t *blk = raw + r * p.raw_slot + slot_off + (e / QK) * BS;
-                            Unpack8<TYPE>::run(blk, (e % QK) >> 3, y);
+                        uint8_t *dst = a_stage + r * 128 + ((c ^ (r & 7)) << 4);
+                        if constexpr (HU::HAS) {
+                            const int pp = e >> 3;                             // K-quants: one block per raw stage
+                            *reinterpret_cast<uint4 *>(dst) = HU::run(raw + r * p.raw_slot + slot_off, pp, tab[r * HU::NSUB + HU::sub_of(pp)]);
                         } else {
+                            float y[8];
+                            if (sb * RAWK + e < p.K) {
+                                const uint8_t *blk = raw + r * p.raw_slot + slot_off + (e / QK) * BS;
+                                Unpack8<TYPE>::run(blk, (e % QK) >> 3, y);
+                            } else {
 #pragma unroll
-                            for (int k = 0; k < 8; k++) y[k] = 0.0f;
+                                for (int k = 0; k < 8; k++) y[k] = 0.0f;
+                            }
+                            store8(reinterpret_cast<__half *>(dst), y);
                         }
-                        store8(reinterpret_cast<__half *>(a_stage + r * 128 + ((c ^ (r & 7)) << 4)), y);
                     }
                     fence_proxy_async();                       // generic-proxy stores -> visible to the UMMA (async proxy)
                     __syncwarp();
@@ -358,6 +375,21 @@ int launch_quantize(const void *X, int64_t M, int64_t K, uint8_t *img, bool d_ha
     return GGB_OK;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver-entry-point query (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(ptr);
+    }();
+    return fn;
+}
+
 template <int TYPE, int BN, typename T>
 int launch_gemm(const void *W, const uint8_t *img, void *Y, int64_t M, int64_t K, int64_t N, int64_t ldy, cudaStream_t stream) {
     constexpr int QK = BlockTraits<TYPE>::QK, BS = BlockTraits<TYPE>::BS;
@@ -376,14 +408,36 @@ int launch_gemm(const void *W, const uint8_t *img, void *Y, int64_t M, int64_t K
     p.Mp = (int)padded_m(M);
     p.n_row_blocks = (int)((N + BM - 1) / BM);
     p.n_tok_tiles = p.Mp / BN;
-    p.raw_slot = (SB_BYTES + 30 + 15) & ~15;
-    const int64_t total = N * (int64_t)p.row_bytes;
-    p.w_fast = ((reinterpret_cast<uintptr_t>(W) & 15) == 0) && (total % 16 == 0);
-    p.w_lo = (int)(reinterpret_cast<uintptr_t>(W) & 15);
+    constexpr int BOX_INNER = (SB_BYTES + ((SB_BYTES % 16) ? 14 : 0) + 15) & ~15;
+    p.raw_slot = BOX_INNER;
+    p.w_fast = ((reinterpret_cast<uintptr_t>(W) & 15) == 0) && (p.row_bytes % 16 == 0);
+    p.w_lo = 0;
+    alignas(64) CUtensorMap tmap;
+    memset(&tmap, 0, sizeof tmap);
+    if (p.w_fast) {
+        EncodeTiledFn enc = get_encode_fn();
+        if (!enc) {
+            ggb_set_error("ggb_mmq: cuTensorMapEncodeTiled is not available from this driver");
+            return GGB_E_CUDA;
+        }
+        // W as a 2-D tensor of uint16 [N rows][row_bytes / 2], box = [128 rows][BOX_INNER / 2]
+        const cuuint64_t gdim[2] = {(cuuint64_t)(p.row_bytes / 2), (cuuint64_t)N};
+        const cuuint64_t gstride[1] = {(cuuint64_t)p.row_bytes};
+        const cuuint32_t box[2] = {(cuuint32_t)(BOX_INNER / 2), (cuuint32_t)BM};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void *>(W), gdim, gstride, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            ggb_set_error("ggb_mmq: cuTensorMapEncodeTiled failed (%d)", (int)r);
+            return GGB_E_CUDA;
+        }
+    }
     p.off_b = NSTAGE * A_STAGE_BYTES;
     p.off_raw = p.off_b + NSTAGE * BN * 128;
     p.off_raw = (p.off_raw + 1023) & ~1023;
-    p.off_bar = (p.off_raw + NRAW * BM * p.raw_slot + 127) & ~127;
+    p.off_tab = (p.off_raw + NRAW * BM * p.raw_slot + 127) & ~127;
+    p.off_bar = (p.off_tab + (HalfUnpack<TYPE>::HAS ? NRAW * BM * HalfUnpack<TYPE>::NSUB * 4 : 0) + 127) & ~127;
     const int smem = p.off_bar + 256 + 1024;     // + slack so the kernel can align its base to 1024
     if (smem > di.max_smem_optin) {
         ggb_set_error("ggb_mmq: tile needs %d bytes of shared memory (limit %d)", smem, di.max_smem_optin);
@@ -396,7 +450,7 @@ int launch_gemm(const void *W, const uint8_t *img, void *Y, int64_t M, int64_t K
     }
     const int64_t ntiles = (int64_t)p.n_row_blocks * p.n_tok_tiles;
     const int grid = (int)(ntiles < di.sm_count ? ntiles : di.sm_count);
-    mmq_kernel<TYPE, BN, T><<<grid, kThreads, smem, stream>>>(p);
+    mmq_kernel<TYPE, BN, T><<<grid, kThreads, smem, stream>>>(p, tmap);
     GGB_CUDA_TRY(cudaGetLastError());
     return GGB_OK;
 }

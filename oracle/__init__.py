@@ -57,6 +57,7 @@ def lib() -> ctypes.CDLL:
         L.orc_q8_1_mmq_bytes.argtypes = [i64, i64]
         L.orc_q8_1_mmq_bytes.restype = i64
         L.orc_quantize_q8_1_mmq.argtypes = [vp, i64, i64, ci, vp]
+        L.orc_mmq_a_operand.argtypes = [vp, ci, i64, vp]
         L.orc_mmvq.argtypes = [vp, ci, vp, i64, i64, i64, vp]
         L.orc_mmq.argtypes = [vp, ci, vp, i64, i64, i64, vp]
         _lib = L
@@ -114,6 +115,17 @@ def quantize_q8_1_mmq(x: np.ndarray, need_sum: bool) -> np.ndarray:
     out = np.zeros(nbytes, dtype=np.uint8)
     lib().orc_quantize_q8_1_mmq(x.ctypes.data, M, K, int(bool(need_sum)), out.ctypes.data)
     return out.reshape(-1, M, 144)
+
+
+def mmq_a_operand(w, qtype: int, m: int, n: int) -> np.ndarray:
+    """fp16 [m, n]: the A operand the MMQ kernel feeds the tensor cores (half-FMA unpack for Q4_K/Q5_K/Q6_K,
+    fp16(dequantize) for the other types); product-defined, used by the operand-exact parity test."""
+    wb = _u8(w)
+    out = np.empty((m, n), dtype=np.float16)
+    rc = lib().orc_mmq_a_operand(wb.ctypes.data, int(qtype), m * n, out.ctypes.data)
+    if rc:
+        raise ValueError(f"orc_mmq_a_operand rc={rc}")
+    return out
 
 
 def mmvq(w, qtype: int, x: np.ndarray, N: int) -> np.ndarray:

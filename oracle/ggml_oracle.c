@@ -356,6 +356,66 @@ int orc_mmq_need_sum(int type) {                     /* mmq.cu:84-106 */
     return type == ORC_Q4_0 || type == ORC_Q4_1 || type == ORC_Q5_1 || type == ORC_Q4_K || type == ORC_Q5_K;
 }
 
+
+/* ------------------------------------------------------------------ MMQ A operand (product-defined, not reference) */
+
+/* round-to-nearest-even double -> binary16 with ONE rounding (used where the exact value is not an fp32) */
+static uint16_t d2h(double x) {
+    if (x != x) return 0x7e00;
+    uint16_t sign = (uint16_t)(signbit(x) ? 0x8000u : 0);
+    double a = fabs(x);
+    if (a == 0.0) return sign;
+    if (a >= 65520.0) return (uint16_t)(sign | 0x7c00u);
+    int e;
+    (void)frexp(a, &e);                       /* a = m * 2^e, m in [0.5, 1)  ->  a in [2^(e-1), 2^e) */
+    int ex = e - 1;
+    if (ex < -14) ex = -14;                    /* subnormal quantum 2^-24 */
+    const double quantum = ldexp(1.0, ex - 10);
+    const double r = nearbyint(a / quantum);   /* default rounding mode: nearest-even */
+    const double v = r * quantum;
+    /* v is exactly representable in binary16 (or rounds up to the next binade, still representable) */
+    return (uint16_t)(sign | f2h((float)v));
+}
+
+/* The fp16 A operand the MMQ kernel feeds the tensor cores (ggml-libtorch_b200/csrc/mmq_unpack.cuh):
+ *   Q4_K, Q5_K: a = fp16( q * fp16(d*sc) - fp16(dmin*m) )   (one fp16 FMA: exact value, single rounding)
+ *   Q6_K      : a = fp16( (q-32) * fp16(d*sc) )
+ *   others    : a = fp16( dequantize(w) )                   (the fp32 dequantizer value, one RN) */
+int orc_mmq_a_operand(const void *w, int type, int64_t nelem, uint16_t *out) {
+    const int qk = orc_block_elems(type), bs = orc_block_bytes(type);
+    if (qk == 0 || type == ORC_Q8_1) return -1;
+    if (nelem % qk) return -2;
+    const uint8_t *p = (const uint8_t *)w;
+    const int64_t nb = nelem / qk;
+    for (int64_t i = 0; i < nb; i++) {
+        const uint8_t *b = p + i * bs;
+        uint16_t *y = out + i * qk;
+        if (type == ORC_Q4_K || type == ORC_Q5_K) {
+            int q[256];
+            unpack_block_ints(type, b, q);
+            const float d = h2f(ld16(b)), dmin = h2f(ld16(b + 2));
+            for (int j = 0; j < 8; j++) {
+                int sc, mn; k4_scale_min(j, b + 4, &sc, &mn);
+                const double dl = h2f(f2h(d * (float)sc)), ml = h2f(f2h(dmin * (float)mn));
+                for (int l = 0; l < 32; l++) y[32 * j + l] = d2h((double)q[32 * j + l] * dl - ml);
+            }
+        } else if (type == ORC_Q6_K) {
+            int q[256];
+            unpack_block_ints(type, b, q);
+            const float d = h2f(ld16(b + 208));
+            for (int is = 0; is < 16; is++) {
+                const double dl = h2f(f2h(d * (float)(int8_t)b[192 + is]));
+                for (int l = 0; l < 16; l++) y[16 * is + l] = d2h((double)q[16 * is + l] * dl);
+            }
+        } else {
+            float f[256];
+            dequant_block(type, b, f);
+            for (int l = 0; l < qk; l++) y[l] = f2h(f[l]);
+        }
+    }
+    return 0;
+}
+
 /* ------------------------------------------------------------------ quantized dot products */
 
 /* One weight row (K elements of `type`) against one activation row given as per-32 groups:

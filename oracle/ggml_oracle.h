@@ -30,6 +30,9 @@ int     orc_quantize_q8_1(const float *x, int64_t rows, int64_t K, void *out);
 int64_t orc_q8_1_mmq_bytes(int64_t M, int64_t K);
 int     orc_quantize_q8_1_mmq(const float *x, int64_t M, int64_t K, int need_sum, void *out);
 
+/* fp16 bit patterns of the A operand the MMQ kernel builds (product-defined; see ggml_oracle.c) */
+int     orc_mmq_a_operand(const void *w, int type, int64_t nelem, uint16_t *out);
+
 int     orc_mmvq(const void *W, int type, const void *q8_1, int64_t B, int64_t K, int64_t N, float *Y);
 int     orc_mmq(const void *W, int type, const void *q8_1_mmq, int64_t M, int64_t K, int64_t N, float *Y);
 

@@ -15,7 +15,7 @@ for t, N, K, M in cases:
     got = ggml.ggml_mul_mat_a8(torch.from_numpy(w).cuda(), x.cuda(), t, N)
     torch.cuda.synchronize()
     got = got.cpu().numpy()
-    a16 = oracle.dequantize(w, t, N, K).astype(np.float16).astype(np.float64)
+    a16 = oracle.mmq_a_operand(w, t, N, K).astype(np.float64)
     b16 = mmq_b_operand_fp16(x.numpy(), oracle.mmq_need_sum(t)).astype(np.float64)
     exact = b16 @ a16.T
     err = np.abs(got - exact)

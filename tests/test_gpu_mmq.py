@@ -40,7 +40,7 @@ def _check(ops, t, N, K, M, dtype, seed=0, dist="randn"):
     got = got.float().cpu().numpy()
     name = f"{oracle.TYPE_NAMES[t]} N={N} K={K} M={M} {dtype}"
     # (b) operand-exact
-    a16 = oracle.dequantize(w, t, N, K).astype(np.float16).astype(np.float64)
+    a16 = oracle.mmq_a_operand(w, t, N, K).astype(np.float64)
     b16 = mmq_b_operand_fp16(x32, oracle.mmq_need_sum(t)).astype(np.float64)
     exact = b16 @ a16.T
     scale = float(np.abs(exact).max()) + 1e-30
