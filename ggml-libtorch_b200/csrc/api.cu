@@ -17,6 +17,8 @@ int64_t ggb_mmvq_workspace_bytes_impl(int type, int64_t B, int64_t K, int64_t N)
 int ggb_mmq_impl(const void *W, const void *X, void *Y, int type, int xy_dtype, int64_t M, int64_t K, int64_t N,
                  int64_t ldy, void *ws, int64_t ws_bytes, cudaStream_t stream);
 int64_t ggb_mmq_workspace_bytes_impl(int type, int64_t M, int64_t K, int64_t N);
+void ggb_mmvq_sb_set_static_weights(int on);
+void ggb_mmvq_sb_tune(int warps, int smem_cap_kb);
 
 // ---------------------------------------------------------------- errors
 static thread_local char g_err[512] = "";
@@ -85,6 +87,21 @@ int ggb_version(void) { return GGB_VERSION; }
 const char *ggb_last_error(void) { return g_err; }
 int ggb_block_elems(int type) { return block_elems(type); }
 int ggb_block_bytes(int type) { return block_bytes(type); }
+
+int ggb_set_option(int option, int value) {
+    g_err[0] = 0;
+    switch (option) {
+        case GGB_OPT_STATIC_WEIGHTS:
+            ggb_mmvq_sb_set_static_weights(value);
+            return GGB_OK;
+        case GGB_OPT_MMVQ_WARPS:
+            ggb_mmvq_sb_tune(value & 0xff, value >> 8);
+            return GGB_OK;
+        default:
+            ggb_set_error("ggb_set_option: unknown option %d", option);
+            return GGB_E_ARG;
+    }
+}
 
 int ggb_dequantize(const void *W, int type, int64_t m, int64_t n, void *out, int out_dtype, void *stream) {
     g_err[0] = 0;

@@ -13,10 +13,11 @@ LIB_PATH = os.environ.get("GGML_B200_LIB", os.path.join(_HERE, "..", "lib", "lib
 
 GGB_F32, GGB_F16, GGB_BF16 = 0, 1, 2
 GGB_Q8_1, GGB_Q8_1_MMQ = 0, 1
+GGB_OPT_STATIC_WEIGHTS = 1
 
 # every symbol include/ggml_b200.h declares (tests check the library exports all of them)
 SYMBOLS = (
-    "ggb_version", "ggb_last_error", "ggb_block_elems", "ggb_block_bytes",
+    "ggb_version", "ggb_last_error", "ggb_set_option", "ggb_block_elems", "ggb_block_bytes",
     "ggb_dequantize", "ggb_q8_1_bytes", "ggb_quantize_q8_1",
     "ggb_mmvq_workspace_bytes", "ggb_mmvq", "ggb_mmq_workspace_bytes", "ggb_mmq",
 )
@@ -36,6 +37,7 @@ def _load() -> ctypes.CDLL:
     i64, vp, ci = ctypes.c_int64, ctypes.c_void_p, ctypes.c_int
     L.ggb_version.restype = ci
     L.ggb_last_error.restype = ctypes.c_char_p
+    L.ggb_set_option.argtypes = [ci, ci]
     L.ggb_block_elems.argtypes = [ci]
     L.ggb_block_bytes.argtypes = [ci]
     L.ggb_dequantize.argtypes = [vp, ci, i64, i64, vp, ci, vp]

@@ -50,6 +50,20 @@ int         ggb_version(void);
 /* Thread-local description of the last failure on this thread ("" if none). */
 const char *ggb_last_error(void);
 
+/*
+ * Process-wide options (no reference counterpart; the reference has no tunables).
+ * GGB_OPT_STATIC_WEIGHTS = 1 declares that weight tensors are never written by work enqueued on the
+ * same stream shortly before a matmul (true for inference weights).  MMVQ launches are programmatic
+ * dependent launches: with this option the weight stream starts while the PREVIOUS kernel on the stream
+ * is still draining (activations are still read, and outputs written, only after it has completed).
+ * Default 0: everything waits for the previous kernel.
+ */
+enum ggb_option {
+    GGB_OPT_STATIC_WEIGHTS = 1,
+    GGB_OPT_MMVQ_WARPS = 2     /* tuning/debug: value = warps (0 auto, 8, 16) | shared-memory cap in KB << 8 */
+};
+int         ggb_set_option(int option, int value);
+
 /* Block geometry of a ggml_type (0 if unsupported).  ggml/ggml-common.h:1163-1240 (qk) / :17-108. */
 int         ggb_block_elems(int type);
 int         ggb_block_bytes(int type);

@@ -1,0 +1,38 @@
+"""Debug: per-CTA timeline of consecutive MMVQ launches inside one CUDA graph (globaltimer stamps)."""
+import os, sys, ctypes
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "ggml-libtorch_b200")]
+import numpy as np, torch
+import ggml
+from ggml import synth, _capi
+opt = dict(a.split("=") for a in sys.argv[1:] if "=" in a)
+static, warps, cap = int(opt.get("static", "1")), int(opt.get("warps", "0")), int(opt.get("cap", "0"))
+N, K, t, B = int(opt.get("N", 14336)), int(opt.get("K", 4096)), int(opt.get("t", 12)), int(opt.get("B", 1))
+L = _capi.lib
+L.ggb_set_option(1, static); L.ggb_set_option(2, warps | (cap << 8))
+L.ggb_debug_mmvq_trace.argtypes = [ctypes.c_void_p]
+dev = torch.device("cuda")
+base = torch.from_numpy(synth.random_blocks(t, N, K, seed=1)).to(dev)
+copies = [base] + [base.clone() for _ in range(5)]
+x = torch.randn(B, K, dtype=torch.float16, device=dev); y = torch.empty(B, N, dtype=torch.float16, device=dev)
+nl = len(copies)
+trace = torch.zeros(64 * 1024, dtype=torch.int64, device=dev)
+s = torch.cuda.Stream()
+with torch.cuda.stream(s):
+    for w in copies: ggml.mul_mat_vec_a8_out(w, x, t, N, y)
+    torch.cuda.synchronize()
+    L.ggb_debug_mmvq_trace(trace.data_ptr())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=s):
+        for w in copies: ggml.mul_mat_vec_a8_out(w, x, t, N, y)
+    L.ggb_debug_mmvq_trace(None)
+    for _ in range(3): g.replay()
+    torch.cuda.synchronize()
+tr = trace.cpu().numpy().reshape(-1, 256, 4)[:nl, :148].astype(np.float64)
+t0 = tr[0, :, 0].min()
+tr = (tr - t0) / 1e3
+print(f"static={static} warps={warps} cap={cap} N={N} K={K} B={B}   (us since first CTA start)")
+for i in range(nl):
+    a = tr[i]
+    print(f"launch {i}: start {a[:,0].min():7.2f}..{a[:,0].max():7.2f}  dep-wait done {a[:,1].min():7.2f}..{a[:,1].max():7.2f}  "
+          f"prologue done {a[:,2].min():7.2f}..{a[:,2].max():7.2f}  end {a[:,3].min():7.2f}..{a[:,3].max():7.2f}")
