@@ -19,6 +19,7 @@ int ggb_mmq_impl(const void *W, const void *X, void *Y, int type, int xy_dtype, 
 int64_t ggb_mmq_workspace_bytes_impl(int type, int64_t M, int64_t K, int64_t N);
 void ggb_mmvq_sb_set_static_weights(int on);
 void ggb_mmvq_sb_tune(int warps, int smem_cap_kb);
+void ggb_mmq_tune(int nb);
 
 // ---------------------------------------------------------------- errors
 static thread_local char g_err[512] = "";
@@ -93,6 +94,9 @@ int ggb_set_option(int option, int value) {
     switch (option) {
         case GGB_OPT_STATIC_WEIGHTS:
             ggb_mmvq_sb_set_static_weights(value);
+            return GGB_OK;
+        case GGB_OPT_MMQ_TILES:
+            ggb_mmq_tune(value);
             return GGB_OK;
         case GGB_OPT_MMVQ_WARPS:
             ggb_mmvq_sb_tune(value & 0xff, value >> 8);

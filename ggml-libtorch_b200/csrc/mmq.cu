@@ -34,8 +34,11 @@ namespace {
 constexpr int BM = 128;              // weight rows per tile (UMMA M)
 constexpr int KSTEP = 64;            // K elements per A/B stage: 128 B of fp16 = one SWIZZLE_128B row
 constexpr int RAWK = 256;            // K elements per raw-weight stage
-constexpr int NSTAGE = 3;
 constexpr int NRAW = 2;
+// NB = token tiles (of BN = 256 tokens) that share one unpacked A stage: 1 -> three A/B stages and a double-buffered
+// accumulator (the epilogue overlaps the next tile); 2 -> every unpacked weight feeds 512 tokens (half the unpack work
+// per MMA), two A/B stages, both 256-column accumulators live in TMEM at once
+__host__ __device__ constexpr int nstage_of(int nb) { return nb == 1 ? 3 : 2; }
 constexpr int kUnpackWarps = 8;
 constexpr int kFirstEpiWarp = 2, kFirstUnpackWarp = 6;
 constexpr int kThreads = (kFirstUnpackWarp + kUnpackWarps) * 32;     // 448
@@ -50,7 +53,7 @@ struct Params {
     int row_bytes;           // bytes per weight row
     int nsb;                 // raw stages per tile = ceil(K / 256)
     int Mp;                  // tokens padded to a multiple of BN
-    int n_row_blocks, n_tok_tiles;
+    int n_row_blocks, n_tok_tiles, n_tok_groups;
     int raw_slot;            // bytes per row in a raw stage
     int w_fast;              // W 16-byte aligned and total bytes % 16 == 0: bulk copies
     int w_lo;                // low 4 bits of W (0 in the fast path)
@@ -71,6 +74,20 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// multicast variants for a thread-block cluster: the arrive / the copied bytes + complete_tx land at the same
+// CTA-relative offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_mc(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -139,15 +156,22 @@ quantize_b_image_kernel(const T *__restrict__ x, uint8_t *__restrict__ img, int6
 }
 
 // ---------------------------------------------------------------- launch 2: the GEMM
-template <int TYPE, int BN, typename T>
+// CL = thread-block cluster size (1 or 2).  The CTAs of a cluster work on CL adjacent 128-row blocks of the SAME
+// token group in lock step: each CTA fetches 1/CL of every B stage and multicasts it to all of them, so the
+// L2 -> SM traffic of the B operand (the limiter at 128 rows per tile) drops by CL.
+template <int TYPE, int BN, int NB, int CL, typename T>
 __global__ void __launch_bounds__(kThreads, 1)
 mmq_kernel(const Params p, const __grid_constant__ CUtensorMap tmapW) {
+    constexpr int NSTAGE = nstage_of(NB);
+    constexpr uint16_t CL_MASK = (uint16_t)((1u << CL) - 1u);
+    constexpr int NACC = (NB == 1) ? 2 : 1;                   // accumulator sets in TMEM
     constexpr int QK = BlockTraits<TYPE>::QK, BS = BlockTraits<TYPE>::BS;
     constexpr int SB_BYTES = RAWK / QK * BS;                  // raw bytes per row per raw stage
     // TMA box width in bytes (also the raw row slot).  The box must START on a 16-byte boundary, so for block sizes
     // that are not multiples of 16 (Q2_K 84, Q3_K 110, Q6_K 210) it starts up to 14 bytes early.
     constexpr int BOX_INNER = (SB_BYTES + ((SB_BYTES % 16) ? 14 : 0) + 15) & ~15;
-    constexpr int B_STAGE_BYTES = BN * 128;
+    constexpr int B_TILE_BYTES = BN * 128;
+    constexpr int B_STAGE_BYTES = NB * B_TILE_BYTES;
     constexpr int ACC_COLS = (BN < 32) ? 32 : BN;             // TMEM columns per accumulator buffer
     constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);   // f16 x f16 -> f32, K-major
 
@@ -165,13 +189,15 @@ mmq_kernel(const Params p, const __grid_constant__ CUtensorMap tmapW) {
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int ntiles = p.n_row_blocks * p.n_tok_tiles;
+    const int n_rbg = (p.n_row_blocks + CL - 1) / CL;          // row-block groups (CL row blocks each; a phantom one is all zeros)
+    const int ntiles = n_rbg * p.n_tok_groups;                // cluster-level tiles
     const int ksteps_total = p.nsb * (RAWK / KSTEP);
+    const int crank = (CL == 1) ? 0 : (int)(blockIdx.x % CL), cid = blockIdx.x / CL, ncl = gridDim.x / CL;
 
     if (tid == 0) {
         for (int s = 0; s < NRAW; s++) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], kUnpackWarps); }
-        for (int s = 0; s < NSTAGE; s++) { mbar_init(&a_full[s], kUnpackWarps); mbar_init(&b_full[s], 1); mbar_init(&ab_empty[s], 1); }
-        for (int s = 0; s < 2; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+        for (int s = 0; s < NSTAGE; s++) { mbar_init(&a_full[s], kUnpackWarps); mbar_init(&b_full[s], 1); mbar_init(&ab_empty[s], CL); }
+        for (int s = 0; s < 2; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }   // NB == 2 uses slot 0 only
         fence_mbar_init();
     }
     if (warp == 1) {   // TMEM: all 512 columns (two accumulator buffers); one CTA per SM so no contention
@@ -179,15 +205,17 @@ mmq_kernel(const Params p, const __grid_constant__ CUtensorMap tmapW) {
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
-    __syncthreads();
+    if (CL == 1) __syncthreads();
+    else cluster_sync_all();                                   // peers' barriers are initialised before anything targets them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         // ============================ producer ============================
         int it = 0, rit = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int rb = tile % p.n_row_blocks, tt = tile / p.n_row_blocks;
+        for (int tile = cid; tile < ntiles; tile += ncl) {
+            const int rb = (tile % n_rbg) * CL + crank, tg = tile / n_rbg;
+            const int tt = tg * NB, nb_valid = min(NB, p.n_tok_tiles - tt);
             const int64_t row0 = (int64_t)rb * BM;
             for (int sb = 0; sb < p.nsb; sb++, rit++) {
                 const int rs = rit % NRAW;
@@ -217,9 +245,15 @@ mmq_kernel(const Params p, const __grid_constant__ CUtensorMap tmapW) {
                     mbar_wait(&ab_empty[s], ((uint32_t)(it / NSTAGE) & 1u) ^ 1u);
                     if (lane == 0) {
                         const int ks = sb * (RAWK / KSTEP) + q;
+                        // the nb_valid token tiles of a group are adjacent in the image: one contiguous copy
                         const uint8_t *src = p.Ximg + ((int64_t)ks * (p.Mp >> 3) + (int64_t)tt * (BN >> 3)) * 1024;
-                        mbar_expect_tx(&b_full[s], B_STAGE_BYTES);
-                        bulk_g2s_plain(sB + s * B_STAGE_BYTES, src, B_STAGE_BYTES, &b_full[s]);
+                        mbar_expect_tx(&b_full[s], (uint32_t)(nb_valid * B_TILE_BYTES));
+                        if (CL == 1) {
+                            bulk_g2s_plain(sB + s * B_STAGE_BYTES, src, (uint32_t)(nb_valid * B_TILE_BYTES), &b_full[s]);
+                        } else {
+                            const uint32_t part = (uint32_t)(nb_valid * B_TILE_BYTES) / CL;
+                            bulk_g2s_mc(sB + s * B_STAGE_BYTES + crank * part, src + crank * part, part, &b_full[s], CL_MASK);
+                        }
                     }
                     __syncwarp();
                 }
@@ -229,9 +263,10 @@ mmq_kernel(const Params p, const __grid_constant__ CUtensorMap tmapW) {
         // ============================ MMA issuer (one thread) ============================
         if (lane == 0) {
             int it = 0, tcount = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
-                const int ab = tcount & 1;
-                mbar_wait(&acc_empty[ab], ((uint32_t)(tcount >> 1) & 1u) ^ 1u);
+            for (int tile = cid; tile < ntiles; tile += ncl, tcount++) {
+                const int ab = tcount % NACC;
+                const int nb_valid = min(NB, p.n_tok_tiles - (tile / n_rbg) * NB);
+                mbar_wait(&acc_empty[ab], ((uint32_t)(tcount / NACC) & 1u) ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(ab * ACC_COLS);
                 for (int ks = 0; ks < ksteps_total; ks++, it++) {
@@ -243,10 +278,15 @@ mmq_kernel(const Params p, const __grid_constant__ CUtensorMap tmapW) {
                     const uint32_t a_addr = smem_u32(sA + s * A_STAGE_BYTES);
                     const uint32_t b_addr = smem_u32(sB + s * B_STAGE_BYTES);
 #pragma unroll
-                    for (int kk = 0; kk < KSTEP / 16; kk++)
+                    for (int kk = 0; kk < KSTEP / 16; kk++) {
                         umma_f16(d_tmem, umma_desc_sw128(a_addr + kk * 32), umma_desc_sw128(b_addr + kk * 32), IDESC,
                                  (ks > 0 || kk > 0) ? 1u : 0u);
-                    umma_commit(&ab_empty[s]);                 // frees the A/B stage when these MMAs retire
+                        if (NB == 2 && nb_valid == 2)
+                            umma_f16(d_tmem + ACC_COLS, umma_desc_sw128(a_addr + kk * 32),
+                                     umma_desc_sw128(b_addr + B_TILE_BYTES + kk * 32), IDESC, (ks > 0 || kk > 0) ? 1u : 0u);
+                    }
+                    if (CL == 1) umma_commit(&ab_empty[s]);    // frees the A/B stage when these MMAs retire
+                    else umma_commit_mc(&ab_empty[s], CL_MASK); // ... in every CTA of the cluster (they multicast into it)
                 }
                 umma_commit(&acc_full[ab]);                    // accumulator complete
             }
@@ -257,25 +297,26 @@ mmq_kernel(const Params p, const __grid_constant__ CUtensorMap tmapW) {
         const int quad = warp & 3;
         T *Y = static_cast<T *>(p.Y);
         int tcount = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
-            const int rb = tile % p.n_row_blocks, tt = tile / p.n_row_blocks;
-            const int ab = tcount & 1;
-            mbar_wait(&acc_full[ab], (uint32_t)(tcount >> 1) & 1u);
+        for (int tile = cid; tile < ntiles; tile += ncl, tcount++) {
+            const int rb = (tile % n_rbg) * CL + crank, tg = tile / n_rbg;
+            const int nb_valid = min(NB, p.n_tok_tiles - tg * NB);
+            const int ab = tcount % NACC;
+            mbar_wait(&acc_full[ab], (uint32_t)(tcount / NACC) & 1u);
             tc_fence_after();
             const int64_t wrow = (int64_t)rb * BM + quad * 32 + lane;
-            const int64_t tok0 = (int64_t)tt * BN;
+            const int64_t tok0 = (int64_t)tg * NB * BN;
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * ACC_COLS);
             constexpr int NCH = (BN + 31) / 32;
 #pragma unroll 1
-            for (int ch = 0; ch < NCH; ch++) {
+            for (int ch = 0; ch < NCH * nb_valid; ch++) {
                 uint32_t v[32];
-                tmem_ld32(taddr + ch * 32, v);
+                tmem_ld32(taddr + ch * 32, v);        // NB == 2: the second accumulator follows at column ACC_COLS == BN
                 tmem_ld_wait();
                 if (wrow < p.N) {
 #pragma unroll
                     for (int j = 0; j < 32; j++) {
                         const int64_t tok = tok0 + ch * 32 + j;
-                        if (ch * 32 + j < BN && tok < p.M) Y[tok * p.ldy + wrow] = from_f32<T>(__uint_as_float(v[j]));
+                        if ((NB == 2 || ch * 32 + j < BN) && tok < p.M) Y[tok * p.ldy + wrow] = from_f32<T>(__uint_as_float(v[j]));
                     }
                 }
             }
@@ -287,8 +328,8 @@ mmq_kernel(const Params p, const __grid_constant__ CUtensorMap tmapW) {
         // ============================ unpack warps: raw GGUF bytes -> fp16 swizzled A tile ============================
         const int u = tid - kFirstUnpackWarp * 32;             // 0..255
         int it = 0, rit = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int rb = tile % p.n_row_blocks;
+        for (int tile = cid; tile < ntiles; tile += ncl) {
+            const int rb = (tile % n_rbg) * CL + crank;
             const int64_t row0 = (int64_t)rb * BM;
             for (int sb = 0; sb < p.nsb; sb++, rit++) {
                 const int rs = rit % NRAW;
@@ -308,6 +349,19 @@ mmq_kernel(const Params p, const __grid_constant__ CUtensorMap tmapW) {
                     const int s = it % NSTAGE;
                     mbar_wait(&ab_empty[s], ((uint32_t)(it / NSTAGE) & 1u) ^ 1u);
                     uint8_t *a_stage = sA + s * A_STAGE_BYTES;
+                    if constexpr (HU::FAST32) {
+                        // one 128-bit load per thread: row r, nibble bytes 16*half..16*half+15 of this k-step
+                        const int r = u >> 1, half = u & 1;
+                        const uint2 sc = *reinterpret_cast<const uint2 *>(tab + r * HU::NSUB + 2 * q);
+                        uint4 o[4];
+                        HU::run32(raw + r * p.raw_slot + slot_off, q, half, sc, o);
+                        uint8_t *row = a_stage + r * 128;
+                        const int sw = r & 7;
+                        *reinterpret_cast<uint4 *>(row + (((2 * half) ^ sw) << 4)) = o[0];
+                        *reinterpret_cast<uint4 *>(row + (((2 * half + 1) ^ sw) << 4)) = o[1];
+                        *reinterpret_cast<uint4 *>(row + (((4 + 2 * half) ^ sw) << 4)) = o[2];
+                        *reinterpret_cast<uint4 *>(row + (((5 + 2 * half) ^ sw) << 4)) = o[3];
+                    } else
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
                         const int item = i * 256 + u;
@@ -340,7 +394,8 @@ mmq_kernel(const Params p, const __grid_constant__ CUtensorMap tmapW) {
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (CL == 1) __syncthreads();
+    else cluster_sync_all();                                   // no CTA leaves while a peer may still signal or copy into it
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
@@ -348,6 +403,7 @@ mmq_kernel(const Params p, const __grid_constant__ CUtensorMap tmapW) {
 }
 
 // ---------------------------------------------------------------- host side
+int g_mmq_cfg = 0;           // tuning bits: 1 = one token tile per weight stage, 2 = no clusters (0 = automatic)
 int pick_bn(int64_t M) {
     if (M > 128) return 256;
     if (M > 64) return 128;
@@ -390,8 +446,10 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-template <int TYPE, int BN, typename T>
+// returns 1 when the configuration does not fit in shared memory (the caller tries the next one)
+template <int TYPE, int BN, int NB, int CL, typename T>
 int launch_gemm(const void *W, const uint8_t *img, void *Y, int64_t M, int64_t K, int64_t N, int64_t ldy, cudaStream_t stream) {
+    constexpr int NSTAGE = nstage_of(NB);
     constexpr int QK = BlockTraits<TYPE>::QK, BS = BlockTraits<TYPE>::BS;
     constexpr int SB_BYTES = RAWK / QK * BS;
     const DeviceInfo &di = ggb_device_info();
@@ -408,6 +466,7 @@ int launch_gemm(const void *W, const uint8_t *img, void *Y, int64_t M, int64_t K
     p.Mp = (int)padded_m(M);
     p.n_row_blocks = (int)((N + BM - 1) / BM);
     p.n_tok_tiles = p.Mp / BN;
+    p.n_tok_groups = (p.n_tok_tiles + NB - 1) / NB;
     constexpr int BOX_INNER = (SB_BYTES + ((SB_BYTES % 16) ? 14 : 0) + 15) & ~15;
     p.raw_slot = BOX_INNER;
     p.w_fast = ((reinterpret_cast<uintptr_t>(W) & 15) == 0) && (p.row_bytes % 16 == 0);
@@ -434,24 +493,37 @@ int launch_gemm(const void *W, const uint8_t *img, void *Y, int64_t M, int64_t K
         }
     }
     p.off_b = NSTAGE * A_STAGE_BYTES;
-    p.off_raw = p.off_b + NSTAGE * BN * 128;
+    p.off_raw = p.off_b + NSTAGE * NB * BN * 128;
     p.off_raw = (p.off_raw + 1023) & ~1023;
     p.off_tab = (p.off_raw + NRAW * BM * p.raw_slot + 127) & ~127;
     p.off_bar = (p.off_tab + (HalfUnpack<TYPE>::HAS ? NRAW * BM * HalfUnpack<TYPE>::NSUB * 4 : 0) + 127) & ~127;
     const int smem = p.off_bar + 256 + 1024;     // + slack so the kernel can align its base to 1024
     if (smem > di.max_smem_optin) {
+        if (NB > 1) return 1;
         ggb_set_error("ggb_mmq: tile needs %d bytes of shared memory (limit %d)", smem, di.max_smem_optin);
         return GGB_E_SHAPE;
     }
     static bool attr_set[64] = {};
     if (!attr_set[di.dev]) {
-        GGB_CUDA_TRY(cudaFuncSetAttribute(mmq_kernel<TYPE, BN, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin));
+        GGB_CUDA_TRY(cudaFuncSetAttribute(mmq_kernel<TYPE, BN, NB, CL, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin));
         attr_set[di.dev] = true;
     }
-    const int64_t ntiles = (int64_t)p.n_row_blocks * p.n_tok_tiles;
-    const int grid = (int)(ntiles < di.sm_count ? ntiles : di.sm_count);
-    mmq_kernel<TYPE, BN, T><<<grid, kThreads, smem, stream>>>(p, tmap);
-    GGB_CUDA_TRY(cudaGetLastError());
+    const int64_t ntiles = (int64_t)((p.n_row_blocks + CL - 1) / CL) * p.n_tok_groups;       // cluster-level tiles
+    const int64_t max_cl = di.sm_count / CL;
+    const int grid = (int)(ntiles < max_cl ? ntiles : max_cl) * CL;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmq_kernel<TYPE, BN, NB, CL, T>, p, tmap));
     return GGB_OK;
 }
 
@@ -460,11 +532,22 @@ int run_typed(const void *W, const void *X, void *Y, int64_t M, int64_t K, int64
     int rc = launch_quantize<T>(X, M, K, img, ggb_mmq_need_sum(TYPE), stream);
     if (rc != GGB_OK) return rc;
     switch (pick_bn(M)) {
-        case 256: return launch_gemm<TYPE, 256, T>(W, img, Y, M, K, N, ldy, stream);
-        case 128: return launch_gemm<TYPE, 128, T>(W, img, Y, M, K, N, ldy, stream);
-        case 64:  return launch_gemm<TYPE, 64, T>(W, img, Y, M, K, N, ldy, stream);
-        case 32:  return launch_gemm<TYPE, 32, T>(W, img, Y, M, K, N, ldy, stream);
-        default:  return launch_gemm<TYPE, 16, T>(W, img, Y, M, K, N, ldy, stream);
+        case 256:
+            // enough tokens for two 256-token tiles per unpacked weight stage, and enough tiles to fill the GPU
+            // enough tokens for two 256-token tiles per unpacked weight stage, and enough tiles to fill the GPU
+            if (M > 256 && (g_mmq_cfg & 1) == 0 &&
+                ((N + BM - 1) / BM) * ((padded_m(M) / 256 + 1) / 2) >= ggb_device_info().sm_count) {
+                rc = (g_mmq_cfg & 2) ? launch_gemm<TYPE, 256, 2, 1, T>(W, img, Y, M, K, N, ldy, stream)
+                                     : launch_gemm<TYPE, 256, 2, 2, T>(W, img, Y, M, K, N, ldy, stream);
+                if (rc != 1) return rc;
+            }
+            if ((g_mmq_cfg & 2) == 0 && (N + BM - 1) / BM * (padded_m(M) / 256) >= ggb_device_info().sm_count)
+                return launch_gemm<TYPE, 256, 1, 2, T>(W, img, Y, M, K, N, ldy, stream);
+            return launch_gemm<TYPE, 256, 1, 1, T>(W, img, Y, M, K, N, ldy, stream);
+        case 128: return launch_gemm<TYPE, 128, 1, 1, T>(W, img, Y, M, K, N, ldy, stream);
+        case 64:  return launch_gemm<TYPE, 64, 1, 1, T>(W, img, Y, M, K, N, ldy, stream);
+        case 32:  return launch_gemm<TYPE, 32, 1, 1, T>(W, img, Y, M, K, N, ldy, stream);
+        default:  return launch_gemm<TYPE, 16, 1, 1, T>(W, img, Y, M, K, N, ldy, stream);
     }
 }
 
@@ -481,6 +564,8 @@ int run_dtype(const void *W, const void *X, void *Y, int dt, int64_t M, int64_t 
 }
 
 }  // namespace
+
+void ggb_mmq_tune(int cfg) { g_mmq_cfg = cfg; }
 
 int64_t ggb_mmq_workspace_bytes_impl(int, int64_t M, int64_t K, int64_t) {
     return padded_k(K) * padded_m(M) * 2;       // the fp16 B-operand image

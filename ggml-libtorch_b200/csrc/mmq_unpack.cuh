@@ -31,11 +31,35 @@ __device__ __forceinline__ uint2 ld_u64_a2(const uint8_t *p) {
     return make_uint2(q[0], q[1]);
 }
 
-template <int TYPE> struct HalfUnpack { static constexpr bool HAS = false; static constexpr int NSUB = 1; };
+// FAST32: the type also provides run32(), which turns one 128-bit load (32 values of one 64-column k-step:
+// 16 consecutive columns + the 16 columns 32 further on) into four 16-byte chunks of the A tile.
+template <int TYPE> struct HalfUnpack { static constexpr bool HAS = false, FAST32 = false; static constexpr int NSUB = 1; };
 
 template <> struct HalfUnpack<T_Q4_K> {
-    static constexpr bool HAS = true;
+    static constexpr bool HAS = true, FAST32 = true;
     static constexpr int NSUB = 8;
+    // k-step q (64 columns = sub-blocks 2q, 2q+1) of a row, bytes 16*half .. 16*half+15 of its 32 nibble bytes:
+    // low nibbles -> columns 16*half + 0..15 (chunks o[0], o[1]), high nibbles -> columns 32 + 16*half + 0..15 (o[2], o[3])
+    __device__ __forceinline__ static void run32(const uint8_t *b, int q, int half, uint2 sc, uint4 (&o)[4]) {
+        const uint4 w = *reinterpret_cast<const uint4 *>(b + 16 + 32 * q + 16 * half);
+        const __half2 dl0 = u32_as_h2(__byte_perm(sc.x, sc.x, 0x1010)), nml0 = u32_as_h2(__byte_perm(sc.x, sc.x, 0x3232));
+        const __half2 dl1 = u32_as_h2(__byte_perm(sc.y, sc.y, 0x1010)), nml1 = u32_as_h2(__byte_perm(sc.y, sc.y, 0x3232));
+        const __half2 k1024 = u32_as_h2(0x64006400u);
+        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+        uint32_t lo[8], hi[8];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t t0 = ww[i] & 0x0f0f0f0fu, t1 = (ww[i] >> 4) & 0x0f0f0f0fu;
+            lo[2 * i] = h2_as_u32(__hfma2(__hsub2(magic_h2_lo(t0), k1024), dl0, nml0));
+            lo[2 * i + 1] = h2_as_u32(__hfma2(__hsub2(magic_h2_hi(t0), k1024), dl0, nml0));
+            hi[2 * i] = h2_as_u32(__hfma2(__hsub2(magic_h2_lo(t1), k1024), dl1, nml1));
+            hi[2 * i + 1] = h2_as_u32(__hfma2(__hsub2(magic_h2_hi(t1), k1024), dl1, nml1));
+        }
+        o[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        o[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+        o[2] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        o[3] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+    }
     __device__ __forceinline__ static int sub_of(int p) { return p >> 2; }
     __device__ __forceinline__ static uint32_t sub_scale(const uint8_t *b, int j) {     // {fp16(dl), -fp16(ml)}
         const float2 s = Unpack8<T_Q4_K>::sub_scale(b, j);
@@ -57,7 +81,7 @@ template <> struct HalfUnpack<T_Q4_K> {
 };
 
 template <> struct HalfUnpack<T_Q5_K> {
-    static constexpr bool HAS = true;
+    static constexpr bool HAS = true, FAST32 = false;
     static constexpr int NSUB = 8;
     __device__ __forceinline__ static int sub_of(int p) { return p >> 2; }
     __device__ __forceinline__ static uint32_t sub_scale(const uint8_t *b, int j) { return HalfUnpack<T_Q4_K>::sub_scale(b, j); }
@@ -79,7 +103,7 @@ template <> struct HalfUnpack<T_Q5_K> {
 };
 
 template <> struct HalfUnpack<T_Q6_K> {
-    static constexpr bool HAS = true;
+    static constexpr bool HAS = true, FAST32 = false;
     static constexpr int NSUB = 16;
     __device__ __forceinline__ static int sub_of(int p) { return p >> 1; }
     __device__ __forceinline__ static uint32_t sub_scale(const uint8_t *b, int is) {     // {fp16(dl), 0}

@@ -60,7 +60,8 @@ const char *ggb_last_error(void);
  */
 enum ggb_option {
     GGB_OPT_STATIC_WEIGHTS = 1,
-    GGB_OPT_MMVQ_WARPS = 2     /* tuning/debug: value = warps (0 auto, 8, 16) | shared-memory cap in KB << 8 */
+    GGB_OPT_MMVQ_WARPS = 2,    /* tuning/debug: value = warps (0 auto, 8, 16) | shared-memory cap in KB << 8 */
+    GGB_OPT_MMQ_TILES = 3      /* tuning/debug bits: 1 = one 256-token tile per weight stage, 2 = no clusters (0 = automatic) */
 };
 int         ggb_set_option(int option, int value);
 
