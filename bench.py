@@ -71,7 +71,7 @@ class Clocks:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -257,9 +257,20 @@ def run_b200(args, rank, local_rank, world):
     out_host = {t: torch.empty((ROWS, COLS), dtype=torch.float16).pin_memory() for t in SWEEP}
     stage = {t: torch.empty_like(w_dev[t]) for t in SWEEP}
 
+    # H2D of the next type's blocks runs on its own stream (its own copy engine) under the dequantize and the
+    # D2H of the current one; every byte still crosses PCIe inside the timed region, every step.
+    s_in = torch.cuda.Stream()
+    staged = {t: torch.cuda.Event() for t in SWEEP}
+
     def e2e_step():
+        main = torch.cuda.current_stream()
+        s_in.wait_stream(main)                      # the previous step's kernels no longer read `stage`
+        with torch.cuda.stream(s_in):
+            for t in SWEEP:
+                stage[t].copy_(w_host[t], non_blocking=True)
+                staged[t].record(s_in)
         for t in SWEEP:
-            stage[t].copy_(w_host[t], non_blocking=True)
+            main.wait_event(staged[t])
             y = ggml.ggml_dequantize(stage[t], t, ROWS, COLS)
             out_host[t].copy_(y, non_blocking=True)
         torch.cuda.synchronize()
@@ -310,7 +321,7 @@ def run_b200(args, rank, local_rank, world):
         "per_type_GBps": {synth.NAMES[t]: (in_bytes[t] + out_bytes) / (kern_ms[t] * 1e-3) / 1e9 for t in SWEEP},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": sum(in_bytes.values()),
                 "d2h_bytes_per_step": out_bytes * len(SWEEP), "steps": e2e_steps,
-                "api": "ggml.ggml_dequantize on pinned-host blocks; result copied back to pinned host"},
+                "api": "ggml.ggml_dequantize on pinned-host blocks (H2D on a second stream), result copied back to pinned host"},
         "gpu_launches": launches,
         "clocks": clk,
         "extras": extras,

@@ -44,10 +44,13 @@ def _time_graph(fn, iters: int, warm: int = 3) -> float:
 def mmvq_section(ggml, synth, dev, peaks, peak_kind):
     hbm = float(peaks["hbm_gbs"])
     out = {"unit": "GB/s (weight bytes / time)", "peak": hbm, "peak_source": peak_kind,
-           "method": "CUDA-graph replay over 8 distinct weight copies per pass (> 2x L2), median of 10 replays, fp16 x/y",
+           "method": "CUDA-graph replay of 4 walks over 8 distinct weight copies (> 2x L2), median of 10 replays, fp16 x/y",
            "cases": []}
     ncopies = 8
+    walks = 4                                # 32 launches per graph replay: the replay's own launch cost is amortised
     launches = 0
+    ggml.set_option(ggml.GGB_OPT_STATIC_WEIGHTS, 1)     # inference weights: the weight stream may start under the previous kernel
+    out["options"] = "GGB_OPT_STATIC_WEIGHTS=1"
     for tname, t in (("Q4_K", 12), ("Q6_K", 14)):
         for (N, K) in ((14336, 4096), (4096, 14336)):
             if t == 14 and N == 14336:
@@ -59,12 +62,15 @@ def mmvq_section(ggml, synth, dev, peaks, peak_kind):
                 x = torch.randn(B, K, dtype=torch.float16, device=dev)
                 y = torch.empty(B, N, dtype=torch.float16, device=dev)
 
-                def run():
-                    for w in copies:
-                        ggml.mul_mat_vec_a8_out(w, x, t, N, y)
+                ws = torch.empty(max(ggml.mmvq_workspace_bytes(t, B, K, N), 16), dtype=torch.uint8, device=dev)
 
-                ms = _time_graph(run, iters=10)
-                launches += ncopies * 14
+                def run():
+                    for _ in range(walks):
+                        for w in copies:
+                            ggml.mul_mat_vec_a8_out(w, x, t, N, y, ws)
+
+                ms = _time_graph(run, iters=10) / walks
+                launches += ncopies * walks * 14
                 gbs = wbytes * ncopies / (ms * 1e-3) / 1e9
                 out["cases"].append({"type": tname, "N": N, "K": K, "B": B, "us_per_launch": ms * 1e3 / ncopies,
                                      "weight_GBps": gbs, "frac_of_hbm_peak": gbs / hbm})
@@ -103,9 +109,68 @@ def mmq_section(ggml, synth, dev, peaks, peak_kind):
     return out, launches
 
 
+def tp_mlp_section(ggml, synth, dev, rank, world, peaks, peak_kind):
+    """BASELINE configs[4]: Llama-3-70B MLP (hidden 8192, intermediate 28672), Q4_K gate/up and Q6_K down,
+    column-parallel over `world` ranks with one NCCL all-gather per projection.  Device time (CUDA events),
+    max over ranks.  Weight GB/s counts every rank's shard bytes (the whole layer) per step."""
+    import torch.distributed as dist
+    from ggml.parallel import ColumnParallelQuantLinear, QuantMLP
+    H, I = 8192, 28672
+    if I % world or H % world:
+        return {"skipped": f"70B MLP does not divide by tp={world}"}, 0
+
+    def shard(t, n_total, k, seed):
+        n_local = n_total // world
+        w = torch.from_numpy(synth.random_blocks(t, n_local, k, seed=seed + 1000 * rank)).to(dev)
+        return ColumnParallelQuantLinear(w, t, n_total, rank, world)
+
+    mlp = QuantMLP(shard(12, I, H, 1), shard(12, I, H, 2), shard(14, H, I, 3))
+    layer_bytes = sum(l.W.numel() for l in (mlp.gate, mlp.up, mlp.down)) * world
+    out = {"unit": "us per MLP block (device time, max over ranks)", "tp": world,
+           "layer": "Llama-3-70B MLP: gate/up [28672, 8192] Q4_K, down [8192, 28672] Q6_K, N-sharded, all-gather per projection",
+           "weight_bytes_total": layer_bytes, "cases": []}
+    launches = 0
+    for M in (1, 8, 512):
+        x = torch.randn(M, H, dtype=torch.float16, device=dev)
+        iters = 20 if M <= 8 else 5
+        for _ in range(3):
+            mlp(x)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            mlp(x)
+        b.record()
+        b.synchronize()
+        ms = a.elapsed_time(b) / iters
+        if world > 1:
+            tm = torch.tensor([ms], device=dev)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            ms = float(tm.item())
+        launches += (iters + 3) * 3
+        case = {"M": M, "us": ms * 1e3}
+        if M <= 8:
+            case["weight_GBps_aggregate"] = layer_bytes / (ms * 1e-3) / 1e9
+            case["frac_of_hbm_peak_per_gpu"] = layer_bytes / world / (ms * 1e-3) / 1e9 / float(peaks["hbm_gbs"])
+        else:
+            case["TOPS_aggregate"] = 2.0 * M * 3 * H * I / (ms * 1e-3) / 1e12
+        out["cases"].append(case)
+    return out, launches
+
+
 def run(ggml, synth, dev, rank, world, peaks, peak_kind):
     extras = {}
     n = 0
+    try:
+        tp, k = tp_mlp_section(ggml, synth, dev, rank, world, peaks, peak_kind)      # every rank takes part
+        n += k
+        if rank == 0:
+            extras["tp_mlp"] = tp
+    except Exception as e:
+        if rank == 0:
+            extras["tp_mlp"] = {"error": f"{type(e).__name__}: {e}"}
     if rank == 0:
         for name, fn in (("mmvq", mmvq_section), ("mmq", mmq_section)):
             try:

@@ -10,14 +10,15 @@
 //      shared memory by ONE bulk asynchronous copy (cp.async.bulk -> TMA engine, mbarrier
 //      completion); 7-8 CTAs are resident per SM so ~50-60 KB of loads are in flight per SM
 //      without any per-thread load instructions or register staging;
-//   2. each thread unpacks items of 8 consecutive output values: super-block scales / minima are
-//      decoded in registers, arithmetic is the CPU op's fp32 order with separately rounded
-//      __fmul_rn / __fadd_rn / __fsub_rn (never contracted into FMA), then ONE round-to-nearest
-//      conversion to the output dtype;
-//   3. every item is written with one 128-bit store (two for fp32); consecutive threads write
-//      consecutive 16-byte chunks, so a warp store covers 512 contiguous bytes.
+//   2. legacy types: each thread unpacks items of 8 consecutive output values; K-quants: the tile's
+//      (d*sc, dmin*m) pairs are decoded once into a table, then each thread takes "column units" = 8
+//      consecutive bytes of a block and all 16 / 32 values packed in them (unpack_col.cuh).  The results
+//      are the CPU op's fp32 arithmetic bit for bit (separately rounded product and sum, never a
+//      contracted multiply-add of the two), then ONE round-to-nearest conversion to the output dtype;
+//   3. every 8 values are written with one 128-bit store (two for fp32); a warp's stores cover whole
+//      64-byte segments.
 // Algorithmic bytes per value: block_bytes/QK read + sizeof(out) written.
-#include "unpack.cuh"
+#include "unpack_col.cuh"
 
 namespace {
 
@@ -60,31 +61,46 @@ dequant_tile_kernel(const uint8_t *__restrict__ W, OutT *__restrict__ out, int64
         __syncthreads();
     }
 
-    // K-quants: decode every (d*sc, dmin*m) pair of the tile ONCE (one or two per thread) instead of once per
-    // 8-value item; the legacy types read their block header inline.
-    constexpr int NSUB = Unpack8<TYPE>::NSUB;
-    constexpr int NTAB = (NSUB > 1) ? TILE_BLOCKS * NSUB : 1;
-    __shared__ float2 sc_tab[NTAB];
-    if constexpr (NSUB > 1) {
-        for (int e = tid; e < nb * NSUB; e += kThreads) sc_tab[e] = Unpack8<TYPE>::sub_scale(tile + (e / NSUB) * BS, e % NSUB);
-        __syncthreads();
-    }
-
-    // item = 8 consecutive values.  Thread t always handles octet p = t % ITEMS_PER_BLOCK of blocks
-    // t / ITEMS_PER_BLOCK + k * BLK_STEP, so everything derived from p (shifts, byte offsets) is loop-invariant;
-    // consecutive threads write consecutive 16-byte chunks (a warp store covers 512 contiguous bytes).
     OutT *dst = out + b0 * QK;
-    constexpr int BLK_STEP = kThreads / ITEMS_PER_BLOCK;
-    static_assert(kThreads % ITEMS_PER_BLOCK == 0 && TILE_BLOCKS % BLK_STEP == 0, "tile/thread geometry");
-    const int p = tid % ITEMS_PER_BLOCK, blk0 = tid / ITEMS_PER_BLOCK;
+    if constexpr (QK == 256) {
+        // K-quants: decode every (d*sc, dmin*m) pair of the tile ONCE into a table, then one "column unit" = 8
+        // consecutive bytes of a block and all the 16 / 32 values packed in them (unpack_col.cuh).
+        using CU = ColUnpack<TYPE>;
+        __shared__ float4 tab[TILE_BLOCKS * CU::NSUB];
+        bool bad = false;
+        for (int e = tid; e < nb * CU::NSUB; e += kThreads) tab[e] = CU::entry(tile + (e / CU::NSUB) * BS, e % CU::NSUB, bad);
+        if (!__syncthreads_or(bad)) {
+            // consecutive threads take consecutive units: a warp's stores cover whole 64-byte segments
 #pragma unroll
-    for (int k = 0; k < TILE_BLOCKS / BLK_STEP; k++) {
-        const int blk = blk0 + k * BLK_STEP;
-        if (blk < nb) {
+            for (int k = 0; k < TILE_BLOCKS * CU::UNITS / kThreads; k++) {
+                const int ug = tid + k * kThreads, blk = ug / CU::UNITS;
+                if (blk < nb) CU::run(tile + blk * BS, ug % CU::UNITS, tab + blk * CU::NSUB, dst + (int64_t)blk * QK);
+            }
+            return;
+        }
+        // a negative / non-finite super-block scale somewhere in the tile: the conversion-based unpacker
+        constexpr int BLK_STEP = kThreads / ITEMS_PER_BLOCK;
+        const int p = tid % ITEMS_PER_BLOCK, blk0 = tid / ITEMS_PER_BLOCK;
+        for (int blk = blk0; blk < nb; blk += BLK_STEP) {
             float y[8];
-            if constexpr (NSUB > 1) Unpack8<TYPE>::run_sc(tile + blk * BS, p, sc_tab[blk * NSUB + Unpack8<TYPE>::sub_of(p)], y);
-            else                    Unpack8<TYPE>::run(tile + blk * BS, p, y);
+            Unpack8<TYPE>::run(tile + blk * BS, p, y);
             store8(dst + ((int64_t)blk * ITEMS_PER_BLOCK + p) * 8, y);
+        }
+    } else {
+        // legacy types.  item = 8 consecutive values.  Thread t always handles octet p = t % ITEMS_PER_BLOCK of blocks
+        // t / ITEMS_PER_BLOCK + k * BLK_STEP, so everything derived from p (shifts, byte offsets) is loop-invariant;
+        // consecutive threads write consecutive 16-byte chunks (a warp store covers 512 contiguous bytes).
+        constexpr int BLK_STEP = kThreads / ITEMS_PER_BLOCK;
+        static_assert(kThreads % ITEMS_PER_BLOCK == 0 && TILE_BLOCKS % BLK_STEP == 0, "tile/thread geometry");
+        const int p = tid % ITEMS_PER_BLOCK, blk0 = tid / ITEMS_PER_BLOCK;
+#pragma unroll
+        for (int k = 0; k < TILE_BLOCKS / BLK_STEP; k++) {
+            const int blk = blk0 + k * BLK_STEP;
+            if (blk < nb) {
+                float y[8];
+                Unpack8<TYPE>::run(tile + blk * BS, p, y);
+                store8(dst + ((int64_t)blk * ITEMS_PER_BLOCK + p) * 8, y);
+            }
         }
     }
 }

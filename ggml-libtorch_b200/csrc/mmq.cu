@@ -350,8 +350,10 @@ mmq_kernel(const Params p, const __grid_constant__ CUtensorMap tmapW) {
                     mbar_wait(&ab_empty[s], ((uint32_t)(it / NSTAGE) & 1u) ^ 1u);
                     uint8_t *a_stage = sA + s * A_STAGE_BYTES;
                     if constexpr (HU::FAST32) {
-                        // one 128-bit load per thread: row r, nibble bytes 16*half..16*half+15 of this k-step
-                        const int r = u >> 1, half = u & 1;
+                        // one 128-bit load per thread: row r, nibble bytes 16*half..16*half+15 of this k-step.  A quarter
+                        // warp = 8 consecutive rows of the same half: its 128-bit loads (row stride 144 B) and its swizzled
+                        // 128-bit stores (chunk ^ (row & 7)) both touch 8 distinct 16-byte bank groups.
+                        const int r = (u & 7) | ((u >> 4) << 3), half = (u >> 3) & 1;
                         const uint2 sc = *reinterpret_cast<const uint2 *>(tab + r * HU::NSUB + 2 * q);
                         uint4 o[4];
                         HU::run32(raw + r * p.raw_slot + slot_off, q, half, sc, o);

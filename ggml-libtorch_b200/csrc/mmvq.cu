@@ -476,17 +476,26 @@ int dispatch_dtype(const void *W, const void *X, void *Y, int dt, int64_t B, int
 
 }  // namespace
 
-int64_t ggb_mmvq_workspace_bytes_impl(int, int64_t, int64_t, int64_t) { return 0; }
+// mmvq_mma.cu: tensor-core integer dots for batches >= 3 (returns 1 when it does not apply)
+int ggb_mmvq_mma_impl(const void *W, const void *X, void *Y, int type, int xy_dtype, int64_t B, int64_t K, int64_t N,
+                      void *ws, int64_t ws_bytes, cudaStream_t stream);
+int64_t ggb_mmvq_mma_workspace_bytes(int type, int64_t B, int64_t K);
+
+int64_t ggb_mmvq_workspace_bytes_impl(int type, int64_t B, int64_t K, int64_t) { return ggb_mmvq_mma_workspace_bytes(type, B, K); }
 
 // mmvq_sb.cu: the super-block-per-lane fast path (returns 1 when it does not apply)
 int ggb_mmvq_sb_impl(const void *W, const void *X, void *Y, int type, int xy_dtype, int64_t B, int64_t K, int64_t N,
                      cudaStream_t stream);
 
 int ggb_mmvq_impl(const void *W, const void *X, void *Y, int type, int xy_dtype, int64_t B, int64_t K, int64_t N,
-                  void *, int64_t, cudaStream_t stream) {
+                  void *ws, int64_t ws_bytes, cudaStream_t stream) {
     if (K > (1 << 24)) {
         ggb_set_error("ggb_mmvq: K=%lld too large", (long long)K);
         return GGB_E_SHAPE;
+    }
+    {
+        const int rc = ggb_mmvq_mma_impl(W, X, Y, type, xy_dtype, B, K, N, ws, ws_bytes, stream);
+        if (rc != 1) return rc;
     }
     {
         const int rc = ggb_mmvq_sb_impl(W, X, Y, type, xy_dtype, B, K, N, stream);

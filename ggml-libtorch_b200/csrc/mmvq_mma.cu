@@ -1,0 +1,557 @@
+// mmvq_mma.cu -- MMVQ for decode batches 3..8: the integer dots run on the tensor cores (mma.sync s8).
+//
+// Same contract as mmvq.cu / mmvq_sb.cu (ggml_mul_mat_vec_a8 = quantize_row_q8_1_cuda + mul_mat_vec_q +
+// vec_dot_*_q8_1; hf-kernels/ggml-kernels/ggml/ggml_kernel.cu:13-66,80-193, ggml/mmvq.cuh:2-209,
+// ggml/vecdotq.cuh:272-349).  The dp4a kernels cost ~4.4 us per batch row on a Llama-8B matrix: above two
+// rows they are instruction-bound, not HBM-bound.  Here one m16n8k32 MMA takes the 32-value integer dots of
+// SIXTEEN weight rows against EIGHT tokens at once, so the cost is the same for every batch size <= 8.
+//
+// Two launches chained by programmatic dependent launch:
+//   (1) mmvq_act_image_kernel: q8_1-quantizes the B x K activations ONCE (bit-identical to quantize_q8_1,
+//       q8_1.cuh) into the caller's workspace, laid out exactly as the GEMV kernel wants it in shared memory.
+//       (In-kernel quantization, as mmvq_sb.cu does for batches 1-2, repeats the work in all 148 CTAs: at
+//       B = 8 that was as many instructions as the GEMV itself.)
+//   (2) mmvq_mma_kernel, one CTA per SM:
+//   * A operand = weights (rows q = lane / 4 and q + 8), B operand = q8_1 activations (token q), both read
+//     straight from shared memory as 64-bit words: the dot product does not care about the order of k, so
+//     lane t = lane % 4 simply owns bytes 8t..8t+7 of each 32-value group on both sides (no ldmatrix, no
+//     transposes).  C gives lane (q, t) the dots of rows q, q + 8 against tokens 2t, 2t + 1.
+//   * Scales stay integers as long as possible: float(sc * dot) comes out of ONE IMAD (the product lands in
+//     the mantissa of 1.5 * 2^23) + one FADD, then one FFMA with the token's d8; d is applied once per
+//     super-block.  The 6-bit scales of a super-block are decoded once per warp (lane (q, t) decodes groups
+//     t, t + 4 of rows q, q + 8 and parks them in a per-warp scratch).
+//   * Minima: sum_g m[row, g] * (d8 * sum q8)[token, g] is a 16 x 8 x 8 GEMM per super-block: two tf32
+//     m16n8k8 MMAs (the fp32 activation factor split in tf32 hi + lo, m is exact), whose A fragment is
+//     exactly the (row, group) pairs the lane decoded itself.
+//   * A CTA owns a contiguous range of rows, cut into row groups of 16.  S = 2^k warps (a team) share a row
+//     group and split K in chunks of `cs` super-blocks (warp s takes chunks s, s + S, ...); the team's
+//     partial sums meet in shared memory and are added in warp order, so the summation order depends on K,
+//     the batch and the type only -- never on N or the grid: N-sharded results stay bit-identical.
+//   * Weights stream through per-warp rings of (16 rows x chunk) slots, ONE 2-D tiled TMA load per slot (a
+//     bulk copy per row costs ~35 instructions each: UBLKCP takes uniform operands), L2 evict-first; the
+//     activation image arrives by bulk copies; programmatic dependent launch and the L2 prefetch of the
+//     weight range are those of mmvq_sb.cu.
+#include "q8_1.cuh"
+#include "tma2d.cuh"
+
+namespace {
+
+constexpr int kMaxSlots = 128;
+constexpr int kRowsPerGroup = 16;
+constexpr int kScrWords = 16 * 8;       // per-warp scratch buffer: 16 rows x {sc[t], sc[t+4]} x 4 lanes (int32)
+
+// Activation image (workspace and shared memory, same layout):
+//   [0, B * act_stride)             int8 quants, token-major, act_stride = K + 32 (conflict-free 64-bit reads)
+//   [off_d, ...)   float2 per (token pair p, group G): {d8[2p][G], d8[2p+1][G]}, pair stride d_stride2 float2
+//   [off_s, ...)   float2 per (token b, group G): tf32 split {hi, lo} of d8 * sum(q8); token stride s_stride2
+struct ActLayout {
+    int act_stride, off_d, d_stride2, off_s, s_stride2, total;
+};
+__host__ __device__ inline ActLayout act_layout(int B, int K) {
+    ActLayout L;
+    const int ng = K / 32, npairs = (B + 1) / 2;
+    L.act_stride = K + 32;
+    L.off_d = (B * L.act_stride + 15) & ~15;
+    L.d_stride2 = ng + 2;                                   // + 16 B: token pairs land in different banks
+    L.off_s = (L.off_d + npairs * L.d_stride2 * 8 + 15) & ~15;
+    L.s_stride2 = ng + 2;
+    L.total = (L.off_s + B * L.s_stride2 * 8 + 15) & ~15;
+    return L;
+}
+
+struct MmaParams {
+    const uint8_t *act_img;  // workspace: the activation image written by mmvq_act_image_kernel
+    void *Y;
+    int64_t N;
+    int K, B;
+    int nsb;               // super-blocks per row
+    int cs;                // super-blocks per chunk
+    int nchunks;
+    int s_log2;            // log2 of the warps per team
+    int slot_row_stride;   // bytes between rows of a slot = chunk bytes (the TMA box is dense)
+    int slot_stride;
+    int depth;             // ring slots per warp
+    int off_scr, off_part, off_slots, off_bars;
+    int row_bytes;
+    unsigned long long *trace;   // debug: per-CTA globaltimer stamps {start, dependency resolved, activations in, end}
+    int pdl_prefetch;
+};
+
+__device__ __forceinline__ uint4 lds128(const void *p) { return *reinterpret_cast<const uint4 *>(p); }
+__device__ __forceinline__ uint2 lds64(const void *p) { return *reinterpret_cast<const uint2 *>(p); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+constexpr int kMagicBits = 0x4B400000;              // 1.5 * 2^23
+constexpr float kMagic = 12582912.0f;
+// exact (float)(a * b): for |a * b| < 2^22 (Q4_K: 32 * 15 * 127 * 63 = 3.84 M) the product lands in the mantissa of
+// 1.5 * 2^23 and one FADD extracts it; Q5_K (up to 7.9 M) takes the conversion instruction
+template <int TYPE>
+__device__ __forceinline__ float imul_to_f32(int a, int b) {
+    if constexpr (TYPE == T_Q4_K) return __int_as_float(a * b + kMagicBits) - kMagic;
+    else return __int2float_rn(a * b);
+}
+
+// int8 dots of 16 weight rows (A: a0/a2 = row q, a1/a3 = row q + 8) against 8 tokens (B) over 32 values
+__device__ __forceinline__ void mma_s8(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%10, %10, %10, %10};"
+        : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(0));
+}
+// tf32 16 x 8 x 8, accumulating
+__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch 1: the activation image
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+mmvq_act_image_kernel(const T *__restrict__ X, uint8_t *__restrict__ img, int B, int K, int x_vec) {
+    pdl_launch_dependents();
+    pdl_wait();                                             // X comes from the previous kernel of the stream
+    const ActLayout L = act_layout(B, K);
+    const int ng = K >> 5;
+    const int t4 = threadIdx.x & 3;
+    const int gi = blockIdx.x * 64 + (threadIdx.x >> 2);    // group index over 2 * npairs tokens (warp-uniform validity per 8 groups)
+    const int ntok = ((B + 1) / 2) * 2;
+    if (gi >= ntok * ng) return;                            // ng is a multiple of 8: whole warps leave together
+    const int b = gi / ng, g = gi - b * ng;
+    float v[8];
+    if (b < B) {
+        load8_f32<T>(X + (int64_t)b * K + g * 32 + t4 * 8, x_vec != 0, v);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = 0.0f;            // the missing token of an odd batch: zero scales
+    }
+    const Q8Group qg = q8_1_quantize_group<false>(v);
+    int sum = __dp4a((int)qg.q_lo, 0x01010101, __dp4a((int)qg.q_hi, 0x01010101, 0));
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    if (b < B) *reinterpret_cast<uint2 *>(img + b * L.act_stride + g * 32 + t4 * 8) = make_uint2(qg.q_lo, qg.q_hi);
+    if (t4 == 0) {
+        const float d8 = __half2float(__float2half_rn(qg.d));
+        reinterpret_cast<float *>(img + L.off_d)[((b >> 1) * L.d_stride2 + g) * 2 + (b & 1)] = d8;
+        if (b < B) {
+            const float s8 = d8 * (float)sum;
+            const float hi = __uint_as_float(__float_as_uint(s8) & 0xffffe000u);
+            reinterpret_cast<float2 *>(img + L.off_s)[b * L.s_stride2 + g] = make_float2(hi, s8 - hi);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-type super-block step.  r0 / r1 = the super-block of weight rows q / q + 8 in the slot; ap = int8
+// activations of token q for this super-block (+ 8t); dp = {d8, d8} pairs of tokens 2t, 2t+1; sp = {hi, lo}
+// of token q; scr = this warp's scratch buffer for this step.
+// ------------------------------------------------------------------------------------------------
+template <int TYPE> struct MmaOps;
+
+// Q4_K / Q5_K header: {d, dmin, 12 bytes of 6-bit (scale, min)} (dequantize.cuh:154-161).  Lane t decodes
+// groups t and t + 4.
+struct K4Head {
+    float d, dmin;
+    int sc_a, sc_b;        // scales of groups t, t + 4
+    uint32_t m_a, m_b;     // minima of groups t, t + 4 as tf32 (exact)
+};
+__device__ __forceinline__ K4Head k4_head(const uint8_t *row, int t) {
+    const uint4 hd = lds128(row);
+    const float2 dm = __half22float2(*reinterpret_cast<const __half2 *>(&hd.x));
+    const uint32_t sh = 8u * t;
+    const uint32_t s0 = (hd.y >> sh) & 0xffu, s1 = (hd.z >> sh) & 0xffu, s2 = (hd.w >> sh) & 0xffu;
+    K4Head h;
+    h.d = dm.x;
+    h.dmin = dm.y;
+    h.sc_a = (int)(s0 & 63u);
+    h.sc_b = (int)((s2 & 15u) | ((s0 >> 6) << 4));
+    h.m_a = __float_as_uint((float)(s1 & 63u));
+    h.m_b = __float_as_uint((float)((s2 >> 4) | ((s1 >> 6) << 4)));
+    return h;
+}
+
+template <int TYPE>
+__device__ __forceinline__ void k45_step(const uint8_t *r0, const uint8_t *r1, const uint8_t *ap, const float2 *dp,
+                                         const float2 *sp, int *scr, int q, int t, float (&acc)[4]) {
+    constexpr int QS = (TYPE == T_Q4_K) ? 16 : 48;          // offset of the nibbles
+    const K4Head h0 = k4_head(r0, t), h1 = k4_head(r1, t);
+    // scales: row-major scratch, 8 ints per row ordered {sc[t], sc[t+4]} by t
+    *reinterpret_cast<int2 *>(scr + q * 8 + 2 * t) = make_int2(h0.sc_a, h0.sc_b);
+    *reinterpret_cast<int2 *>(scr + (q + 8) * 8 + 2 * t) = make_int2(h1.sc_a, h1.sc_b);
+    // minima: C[row, token] += m[row, g] * s8[token, g] over the 8 groups (tf32 hi + lo)
+    float cm[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    {
+        const float2 sa = sp[t], sb = sp[t + 4];
+        mma_tf32(cm, h0.m_a, h1.m_a, h0.m_b, h1.m_b, __float_as_uint(sa.x), __float_as_uint(sb.x));
+        mma_tf32(cm, h0.m_a, h1.m_a, h0.m_b, h1.m_b, __float_as_uint(sa.y), __float_as_uint(sb.y));
+    }
+    __syncwarp();
+    int sc0[8], sc1[8];                                      // sc0[2j] = group j, sc0[2j+1] = group j + 4 (row q); sc1: row q + 8
+    {
+        const int4 a = *reinterpret_cast<const int4 *>(scr + q * 8), b = *reinterpret_cast<const int4 *>(scr + q * 8 + 4);
+        const int4 c = *reinterpret_cast<const int4 *>(scr + (q + 8) * 8), d = *reinterpret_cast<const int4 *>(scr + (q + 8) * 8 + 4);
+        sc0[0] = a.x; sc0[1] = a.y; sc0[2] = a.z; sc0[3] = a.w; sc0[4] = b.x; sc0[5] = b.y; sc0[6] = b.z; sc0[7] = b.w;
+        sc1[0] = c.x; sc1[1] = c.y; sc1[2] = c.z; sc1[3] = c.w; sc1[4] = d.x; sc1[5] = d.y; sc1[6] = d.z; sc1[7] = d.w;
+    }
+    uint2 qh0, qh1;
+    if constexpr (TYPE == T_Q5_K) {                         // fifth bits: bit g of byte j belongs to group g
+        qh0 = lds64(r0 + 16 + 8 * t);
+        qh1 = lds64(r1 + 16 + 8 * t);
+    }
+    float fs[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {                           // groups 2i (low nibbles) and 2i + 1 (high nibbles)
+        const uint2 w0 = lds64(r0 + QS + 32 * i + 8 * t), w1 = lds64(r1 + QS + 32 * i + 8 * t);
+        const uint2 b0 = lds64(ap + 64 * i), b1 = lds64(ap + 64 * i + 32);
+        const float4 d8 = *reinterpret_cast<const float4 *>(dp + 2 * i);      // {d8a[2i], d8b[2i], d8a[2i+1], d8b[2i+1]}
+        uint32_t l0x = w0.x & 0x0f0f0f0fu, l1x = w1.x & 0x0f0f0f0fu, l0y = w0.y & 0x0f0f0f0fu, l1y = w1.y & 0x0f0f0f0fu;
+        uint32_t h0x = (w0.x >> 4) & 0x0f0f0f0fu, h1x = (w1.x >> 4) & 0x0f0f0f0fu;
+        uint32_t h0y = (w0.y >> 4) & 0x0f0f0f0fu, h1y = (w1.y >> 4) & 0x0f0f0f0fu;
+        if constexpr (TYPE == T_Q5_K) {
+            l0x |= ((qh0.x >> (2 * i)) & 0x01010101u) << 4;      l1x |= ((qh1.x >> (2 * i)) & 0x01010101u) << 4;
+            l0y |= ((qh0.y >> (2 * i)) & 0x01010101u) << 4;      l1y |= ((qh1.y >> (2 * i)) & 0x01010101u) << 4;
+            h0x |= ((qh0.x >> (2 * i + 1)) & 0x01010101u) << 4;  h1x |= ((qh1.x >> (2 * i + 1)) & 0x01010101u) << 4;
+            h0y |= ((qh0.y >> (2 * i + 1)) & 0x01010101u) << 4;  h1y |= ((qh1.y >> (2 * i + 1)) & 0x01010101u) << 4;
+        }
+        int cl[4], ch[4];
+        mma_s8(cl, l0x, l1x, l0y, l1y, b0.x, b0.y);
+        mma_s8(ch, h0x, h1x, h0y, h1y, b1.x, b1.y);
+        // group g lives at scratch index 2 * (g & 3) + (g >> 2)
+        const int g0 = 2 * i, g1 = 2 * i + 1;
+        const int i0 = 2 * (g0 & 3) + (g0 >> 2), i1 = 2 * (g1 & 3) + (g1 >> 2);
+        fs[0] = fmaf(d8.x, imul_to_f32<TYPE>(cl[0], sc0[i0]), fs[0]);
+        fs[1] = fmaf(d8.y, imul_to_f32<TYPE>(cl[1], sc0[i0]), fs[1]);
+        fs[2] = fmaf(d8.x, imul_to_f32<TYPE>(cl[2], sc1[i0]), fs[2]);
+        fs[3] = fmaf(d8.y, imul_to_f32<TYPE>(cl[3], sc1[i0]), fs[3]);
+        fs[0] = fmaf(d8.z, imul_to_f32<TYPE>(ch[0], sc0[i1]), fs[0]);
+        fs[1] = fmaf(d8.w, imul_to_f32<TYPE>(ch[1], sc0[i1]), fs[1]);
+        fs[2] = fmaf(d8.z, imul_to_f32<TYPE>(ch[2], sc1[i1]), fs[2]);
+        fs[3] = fmaf(d8.w, imul_to_f32<TYPE>(ch[3], sc1[i1]), fs[3]);
+    }
+    acc[0] += h0.d * fs[0] - h0.dmin * cm[0];
+    acc[1] += h0.d * fs[1] - h0.dmin * cm[1];
+    acc[2] += h1.d * fs[2] - h1.dmin * cm[2];
+    acc[3] += h1.d * fs[3] - h1.dmin * cm[3];
+}
+
+template <> struct MmaOps<T_Q4_K> {
+    static constexpr int BS = 144;
+    __device__ __forceinline__ static void step(const uint8_t *r0, const uint8_t *r1, const uint8_t *ap, const float2 *dp,
+                                                const float2 *sp, int *scr, int q, int t, float (&acc)[4]) {
+        k45_step<T_Q4_K>(r0, r1, ap, dp, sp, scr, q, t, acc);
+    }
+};
+template <> struct MmaOps<T_Q5_K> {
+    static constexpr int BS = 176;
+    __device__ __forceinline__ static void step(const uint8_t *r0, const uint8_t *r1, const uint8_t *ap, const float2 *dp,
+                                                const float2 *sp, int *scr, int q, int t, float (&acc)[4]) {
+        k45_step<T_Q5_K>(r0, r1, ap, dp, sp, scr, q, t, acc);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// launch 2: the GEMV
+// ------------------------------------------------------------------------------------------------
+template <int TYPE, typename T, int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
+mmvq_mma_kernel(const MmaParams p, const __grid_constant__ CUtensorMap tmapW) {
+    using Ops = MmaOps<TYPE>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const ActLayout L = act_layout(p.B, p.K);
+    int *scr_all = reinterpret_cast<int *>(smem + p.off_scr);                   // [NW][2][kScrWords]
+    float4 *part = reinterpret_cast<float4 *>(smem + p.off_part);               // [2][NW][32]
+    uint8_t *slots = smem + p.off_slots;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + p.off_bars);
+    uint64_t *act_full = full + kMaxSlots;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = lane >> 2, t = lane & 3;
+    const int nsb = p.nsb;
+
+    // this CTA's contiguous range of row groups
+    const int64_t ngr_total = (p.N + kRowsPerGroup - 1) / kRowsPerGroup;
+    const int64_t g_begin = ngr_total * (int64_t)blockIdx.x / gridDim.x;
+    const int64_t g_end = ngr_total * (int64_t)(blockIdx.x + 1) / gridDim.x;
+    const int64_t r_begin = g_begin * kRowsPerGroup;
+    const int64_t r_end = min(g_end * kRowsPerGroup, p.N);
+    const int nrows = (int)(r_end - r_begin);
+    const int nrg = (int)(g_end - g_begin);
+
+    const int nslots = NW * p.depth;
+    if (tid < nslots) mbar_init(&full[tid], 1);
+    if (tid == 0) mbar_init(act_full, 1);
+    fence_mbar_init();
+    __syncthreads();
+    pdl_launch_dependents();
+    if (p.trace && tid == 0) p.trace[blockIdx.x * 4 + 0] = gtime();
+
+    const int S = 1 << p.s_log2, NT = NW >> p.s_log2;
+    const int team = warp >> p.s_log2, s = warp & (S - 1);
+    const int my_rgs = (nrg - team + NT - 1) / NT;                 // may be <= 0
+    const int my_chunks = (p.nchunks - s + S - 1) >> p.s_log2;      // >= 1 (S <= nchunks)
+    const int my_units = my_rgs > 0 ? my_rgs * my_chunks : 0;
+    const int ring_base = warp * p.depth;
+    const uint64_t pol = l2_policy_evict_first();
+
+    // issue state, warp-uniform: the next unit (row group, chunk) of this warp to stream
+    int is_k = 0, is_ring = ring_base, is_rg = team, is_c = s;
+    auto issue_next = [&]() {                                      // whole warp (lane 0 issues)
+        if (lane == 0) {
+            // rows past N and bytes past the row end are zero-filled by the TMA unit and count as transferred
+            mbar_expect_tx(&full[is_ring], (uint32_t)(kRowsPerGroup * p.slot_row_stride));
+            tma_load_2d_hint(slots + is_ring * p.slot_stride, &tmapW, (is_c * p.slot_row_stride) >> 2,
+                             (int)r_begin + is_rg * kRowsPerGroup, &full[is_ring], pol);
+        }
+        is_c += S;
+        if (is_c >= p.nchunks) { is_c = s; is_rg += NT; }
+        is_k++;
+        if (++is_ring == ring_base + p.depth) is_ring = ring_base;
+    };
+
+    if (p.pdl_prefetch)
+        while (is_k < min(p.depth, my_units)) issue_next();
+    pdl_wait();                                                    // the activation image is complete
+    if (p.trace && tid == 0) p.trace[blockIdx.x * 4 + 1] = gtime();
+    if (warp == NW - 1 && lane == 0) {                             // (the last warp has the fewest units to prime)
+        mbar_expect_tx(act_full, (uint32_t)L.total);
+        constexpr int kPiece = 32768;
+        for (int off = 0; off < L.total; off += kPiece)
+            bulk_g2s(smem + off, p.act_img + off, (uint32_t)min(kPiece, L.total - off), act_full);
+    }
+    if (!p.pdl_prefetch)
+        while (is_k < min(p.depth, my_units)) issue_next();
+    mbar_wait(act_full, 0);
+    if (p.trace && tid == 0) p.trace[blockIdx.x * 4 + 2] = gtime();
+
+    // ===================== row groups of 16, K split over the team =====================
+    T *Y = static_cast<T *>(p.Y);
+    const int qc = min(q, p.B - 1);                                // lanes of absent tokens shadow the last one
+    const int tc = min(t, (p.B - 1) >> 1);                         // ... and absent token pairs the last pair
+    const uint8_t *act_tok = smem + qc * L.act_stride + 8 * t;
+    const float2 *d_pair = reinterpret_cast<const float2 *>(smem + L.off_d) + tc * L.d_stride2;
+    const float2 *s_tok = reinterpret_cast<const float2 *>(smem + L.off_s) + qc * L.s_stride2;
+    int *scr = scr_all + warp * (2 * kScrWords);
+    int ring = ring_base;
+    uint32_t phase = 0;
+    int step_no = 0;
+    for (int rgi = 0; rgi < my_rgs; rgi++) {
+        const int rg = team + rgi * NT;
+        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        for (int c = s; c < p.nchunks; c += S) {
+            const int sb0 = c * p.cs;
+            const int nsbc = min(p.cs, nsb - sb0);
+            mbar_wait(&full[ring], phase);
+            const uint8_t *r0 = slots + ring * p.slot_stride + q * p.slot_row_stride;
+            const uint8_t *r1 = r0 + 8 * p.slot_row_stride;
+#pragma unroll 1
+            for (int i = 0; i < nsbc; i++) {
+                const int sb = sb0 + i;
+                Ops::step(r0 + i * Ops::BS, r1 + i * Ops::BS, act_tok + sb * 256, d_pair + sb * 8, s_tok + sb * 8,
+                          scr + (step_no & 1) * kScrWords, q, t, acc);
+                step_no++;
+            }
+            __syncwarp();
+            if (is_k < my_units) {                                 // recycle the slot: every lane has finished reading it
+                if (lane == 0) fence_proxy_async();
+                issue_next();
+            }
+            if (++ring == ring_base + p.depth) { ring = ring_base; phase ^= 1u; }
+        }
+        // partial sums of the team's warps meet in shared memory and are added in warp order
+        if (S > 1) {
+            float4 *pb = part + (rgi & 1) * (NW * 32);
+            pb[warp * 32 + lane] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            named_bar_sync(1 + team, S * 32);
+            if (s == 0) {
+                const float4 *src = pb + (team << p.s_log2) * 32 + lane;
+                float4 v = src[0];
+                for (int j = 1; j < S; j++) {
+                    const float4 w = src[j * 32];
+                    v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+                }
+                acc[0] = v.x; acc[1] = v.y; acc[2] = v.z; acc[3] = v.w;
+            }
+        }
+        if (s == 0) {
+            const int lr = rg * kRowsPerGroup + q;
+            const int tok = 2 * t;
+            if (lr < nrows) {
+                if (tok < p.B) Y[(int64_t)tok * p.N + r_begin + lr] = from_f32<T>(acc[0]);
+                if (tok + 1 < p.B) Y[(int64_t)(tok + 1) * p.N + r_begin + lr] = from_f32<T>(acc[1]);
+            }
+            if (lr + 8 < nrows) {
+                if (tok < p.B) Y[(int64_t)tok * p.N + r_begin + lr + 8] = from_f32<T>(acc[2]);
+                if (tok + 1 < p.B) Y[(int64_t)(tok + 1) * p.N + r_begin + lr + 8] = from_f32<T>(acc[3]);
+            }
+        }
+    }
+    if (p.trace && tid == 0) p.trace[blockIdx.x * 4 + 3] = gtime();
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+int g_cs = 0, g_s_log2 = -1;          // tuning overrides (0 / -1 = automatic)
+int g_min_batch = 3;                  // batches below this stay on the dp4a kernels
+
+}  // namespace
+
+int ggb_mmvq_static_weights();        // mmvq_sb.cu
+unsigned long long *ggb_mmvq_trace_slot();
+
+namespace {
+
+// fills p and the shared-memory size for NW warps and `cs` super-blocks per chunk; false if the ring would be too shallow
+template <int TYPE>
+bool plan(MmaParams &p, int &smem, int NW, int cs, int B, int K, int max_smem) {
+    using Ops = MmaOps<TYPE>;
+    const ActLayout L = act_layout(B, K);
+    p.cs = cs < p.nsb ? cs : p.nsb;
+    const int rs = p.cs * Ops::BS;
+    if (rs % 16 != 0 || rs > 1024) return false;               // chunk starts 16-byte aligned; TMA box <= 256 uint32
+    p.nchunks = (p.nsb + p.cs - 1) / p.cs;
+    int sl = 0;
+    while ((2 << sl) <= p.nchunks && (2 << sl) <= NW) sl++;      // S = largest power of two <= min(nchunks, NW)
+    if (g_s_log2 >= 0 && (1 << g_s_log2) <= p.nchunks && (1 << g_s_log2) <= NW) sl = g_s_log2;
+    p.s_log2 = sl;
+    p.slot_row_stride = rs;
+    p.slot_stride = (kRowsPerGroup * rs + 127) & ~127;
+    p.off_scr = (L.total + 127) & ~127;
+    p.off_part = p.off_scr + NW * 2 * kScrWords * 4;
+    p.off_slots = (p.off_part + 2 * NW * 32 * 16 + 127) & ~127;
+    const int bar_bytes = (kMaxSlots + 1) * 8;
+    const int avail = max_smem - p.off_slots - bar_bytes - 128;
+    int depth = avail / (p.slot_stride * NW);
+    if (depth < 2) return false;
+    if (depth > kMaxSlots / NW) depth = kMaxSlots / NW;
+    if (depth > 6) depth = 6;
+    p.depth = depth;
+    p.off_bars = (p.off_slots + NW * depth * p.slot_stride + 127) & ~127;
+    smem = p.off_bars + bar_bytes;
+    return true;
+}
+
+template <int TYPE, typename T, int NW>
+int launch_gemv(MmaParams &p, int smem, const CUtensorMap &tmap, cudaStream_t stream) {
+    const DeviceInfo &di = ggb_device_info();
+    static bool attr_set[64] = {};
+    if (!attr_set[di.dev]) {
+        GGB_CUDA_TRY(cudaFuncSetAttribute(mmvq_mma_kernel<TYPE, T, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          di.max_smem_optin));
+        attr_set[di.dev] = true;
+    }
+    const int64_t ngr = (p.N + kRowsPerGroup - 1) / kRowsPerGroup;
+    const int grid = (int)(ngr < di.sm_count ? ngr : di.sm_count);
+    p.trace = ggb_mmvq_trace_slot();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NW * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmvq_mma_kernel<TYPE, T, NW>, p, tmap));
+    return GGB_OK;
+}
+
+template <int TYPE, typename T>
+int launch(const void *W, const void *X, void *Y, int64_t B, int64_t K, int64_t N, void *ws, cudaStream_t stream) {
+    using Ops = MmaOps<TYPE>;
+    const DeviceInfo &di = ggb_device_info();
+    MmaParams p;
+    p.act_img = static_cast<const uint8_t *>(ws);
+    p.Y = Y;
+    p.N = N;
+    p.K = (int)K;
+    p.B = (int)B;
+    p.nsb = (int)(K / 256);
+    p.row_bytes = p.nsb * Ops::BS;
+    p.pdl_prefetch = ggb_mmvq_static_weights();
+    if (p.row_bytes % 16 != 0 || N > 0x7fffffff) return 1;
+    // preferred chunk: 2 super-blocks for short rows (more K-parallelism), 4 for long ones; smaller if the ring needs it
+    const int pref = g_cs > 0 ? g_cs : (p.nsb <= 16 ? 2 : 4);
+    int smem = 0, nw = 0;
+    for (int NW : {16, 8}) {
+        for (int cs = pref; cs >= 1 && !nw; cs >>= 1)
+            if (plan<TYPE>(p, smem, NW, cs, (int)B, (int)K, di.max_smem_optin)) nw = NW;
+        if (nw) break;
+    }
+    if (!nw) return 1;
+    alignas(64) CUtensorMap tmap;
+    {
+        const int rc = ggb_make_row_tensor_map(&tmap, W, N, p.row_bytes, kRowsPerGroup, p.slot_row_stride, "ggb_mmvq");
+        if (rc != GGB_OK) return rc;
+    }
+    // launch 1: the activation image
+    {
+        const int ntok = (int)((B + 1) / 2) * 2;
+        const int ngroups = ntok * (int)(K / 32);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((ngroups + 63) / 64);
+        cfg.blockDim = dim3(256);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        const int x_vec = (reinterpret_cast<uintptr_t>(X) & 15) == 0;
+        GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmvq_act_image_kernel<T>, static_cast<const T *>(X), static_cast<uint8_t *>(ws),
+                                        (int)B, (int)K, x_vec));
+    }
+    return nw == 16 ? launch_gemv<TYPE, T, 16>(p, smem, tmap, stream) : launch_gemv<TYPE, T, 8>(p, smem, tmap, stream);
+}
+
+template <int TYPE>
+int dispatch_dtype(const void *W, const void *X, void *Y, int dt, int64_t B, int64_t K, int64_t N, void *ws, cudaStream_t stream) {
+    switch (dt) {
+        case GGB_F32:  return launch<TYPE, float>(W, X, Y, B, K, N, ws, stream);
+        case GGB_F16:  return launch<TYPE, __half>(W, X, Y, B, K, N, ws, stream);
+        case GGB_BF16: return launch<TYPE, __nv_bfloat16>(W, X, Y, B, K, N, ws, stream);
+        default: return 1;
+    }
+}
+
+bool mma_applies(int type, int64_t B, int64_t K) {
+    return (type == T_Q4_K || type == T_Q5_K) && B >= g_min_batch && B <= 8 && K % 256 == 0 && K <= (1 << 16);
+}
+
+}  // namespace
+
+void ggb_mmvq_mma_tune(int cs, int s_log2_plus1, int min_batch) {
+    g_cs = cs;
+    g_s_log2 = s_log2_plus1 - 1;
+    if (min_batch > 0) g_min_batch = min_batch;
+}
+
+// workspace for the activation image (0 when this path does not apply)
+int64_t ggb_mmvq_mma_workspace_bytes(int type, int64_t B, int64_t K) {
+    if (!mma_applies(type, B, K)) return 0;
+    return act_layout((int)B, (int)K).total;
+}
+
+// returns GGB_OK / a negative status, or 1 when this path does not apply (the caller tries mmvq_sb.cu, then mmvq.cu)
+int ggb_mmvq_mma_impl(const void *W, const void *X, void *Y, int type, int xy_dtype, int64_t B, int64_t K, int64_t N,
+                      void *ws, int64_t ws_bytes, cudaStream_t stream) {
+    if (!mma_applies(type, B, K) || (reinterpret_cast<uintptr_t>(W) & 15)) return 1;
+    if (!ws || (reinterpret_cast<uintptr_t>(ws) & 15) || ws_bytes < act_layout((int)B, (int)K).total) return 1;
+    switch (type) {
+        case T_Q4_K: return dispatch_dtype<T_Q4_K>(W, X, Y, xy_dtype, B, K, N, ws, stream);
+        case T_Q5_K: return dispatch_dtype<T_Q5_K>(W, X, Y, xy_dtype, B, K, N, ws, stream);
+        default: return 1;
+    }
+}

@@ -16,11 +16,13 @@ from __future__ import annotations
 import torch
 
 from . import _capi
-from ._capi import GGB_BF16, GGB_F16, GGB_F32, GGB_Q8_1, GGB_Q8_1_MMQ, GgmlB200Error  # noqa: F401
+from ._capi import (GGB_BF16, GGB_F16, GGB_F32, GGB_OPT_STATIC_WEIGHTS, GGB_Q8_1, GGB_Q8_1_MMQ,  # noqa: F401
+                    GgmlB200Error)
 
 __all__ = [
     "ggml_dequantize", "ggml_mul_mat_vec_a8", "ggml_mul_mat_a8", "ggml_quantize_q8_1",
-    "dequantize_out", "mul_mat_vec_a8_out", "mul_mat_a8_out", "mmq_workspace_bytes",
+    "dequantize_out", "mul_mat_vec_a8_out", "mul_mat_a8_out", "mmq_workspace_bytes", "mmvq_workspace_bytes",
+    "set_option", "GGB_OPT_STATIC_WEIGHTS",
     "block_elems", "block_bytes", "SUPPORTED_TYPES", "MMVQ_MAX_BATCH",
 ]
 
@@ -31,6 +33,12 @@ _DT_INV = {v: k for k, v in _DT.items()}
 # ggml_type ids, ggml/ggml-common.h:1128-1161
 SUPPORTED_TYPES = (2, 3, 6, 7, 8, 10, 11, 12, 13, 14)
 MMVQ_MAX_BATCH = 8
+
+
+def set_option(option: int, value: int) -> None:
+    """Process-wide library options (include/ggml_b200.h `enum ggb_option`); e.g. GGB_OPT_STATIC_WEIGHTS = 1
+    declares inference weights immutable so the MMVQ weight stream may start under the previous kernel."""
+    _capi.check(_lib.ggb_set_option(int(option), int(value)), "ggb_set_option")
 
 
 def block_elems(quant_type: int) -> int:

@@ -18,6 +18,11 @@ static = int(opt.get("static", "0"))
 _capi.lib.ggb_set_option(_capi.GGB_OPT_STATIC_WEIGHTS, static)
 warps, cap = int(opt.get("warps", "0")), int(opt.get("cap", "0"))
 _capi.lib.ggb_set_option(2, warps | (cap << 8))
+if "mma" in opt:      # cs,s_log2+1,min_batch
+    a, b, c = (int(v) for v in opt["mma"].split(","))
+    _capi.lib.ggb_set_option(5, a | (b << 8) | (c << 16))
+l2 = int(opt.get("l2", "0"))
+_capi.lib.ggb_set_option(4, l2)
 shapes = ((14336, 4096), (4096, 14336), (28672, 8192), (8192, 28672))
 if "shapes" in opt:
     shapes = tuple(tuple(int(v) for v in sh.split("x")) for sh in opt["shapes"].split(","))
@@ -25,7 +30,7 @@ if "shapes" in opt:
 if "check" in args or not [a for a in args if "=" not in a]:
     for t in types:
         for (N, K, B) in [(1, 256, 1), (5, 512, 3), (96, 1024, 2), (300, 4096, 1), (64, 6144, 3), (33, 2304, 2), (257, 2048, 8),
-                          (257, 2048, 5), (1000, 14336, 1), (999, 8192, 4), (14336, 4096, 1)]:
+                          (257, 2048, 5), (1000, 14336, 1), (999, 8192, 4), (14336, 4096, 1), (14336, 4096, 8), (4096, 14336, 3), (1001, 2304, 7)]:
             w = oracle.random_weights(t, N, K, seed=1)
             x = torch.randn(B, K, generator=torch.Generator().manual_seed(0))
             want = oracle.mmvq(w, t, x.numpy(), N)
@@ -40,7 +45,7 @@ if "time" in args:
     for t in types:
         for (N, K) in shapes:
             base = torch.from_numpy(synth.random_blocks(t, N, K, seed=N + t)).to(dev)
-            ncopies = max(2, min(8, int(600e6 // base.numel())))
+            ncopies = int(opt.get("copies", max(2, min(8, int(600e6 // base.numel())))))
             copies = [base] + [base.clone() for _ in range(ncopies - 1)]
             reps = int(opt.get("reps", "1"))             # launches per graph = ncopies * reps
             for B in batches:
@@ -66,6 +71,6 @@ if "time" in args:
                         ts.append(a.elapsed_time(b))
                 ms = statistics.median(ts)
                 us = ms * 1e3 / (ncopies * reps)
-                print(f"type {t} N={N} K={K} B={B} static={static} warps={warps} cap={cap} reps={reps}: {us:.2f} us/launch  {base.numel()/us/1e3:.0f} GB/s "
+                print(f"type {t} N={N} K={K} B={B} static={static} l2={l2} warps={warps} cap={cap} reps={reps}: {us:.2f} us/launch  {base.numel()/us/1e3:.0f} GB/s "
                       f"({base.numel()/us/1e3/6552.3*100:.1f}% of 6552)", flush=True)
             del copies, base

@@ -10,6 +10,7 @@ static, warps, cap = int(opt.get("static", "1")), int(opt.get("warps", "0")), in
 N, K, t, B = int(opt.get("N", 14336)), int(opt.get("K", 4096)), int(opt.get("t", 12)), int(opt.get("B", 1))
 L = _capi.lib
 L.ggb_set_option(1, static); L.ggb_set_option(2, warps | (cap << 8))
+l2 = int(opt.get("l2", "0")); L.ggb_set_option(4, l2)
 L.ggb_debug_mmvq_trace.argtypes = [ctypes.c_void_p]
 dev = torch.device("cuda")
 base = torch.from_numpy(synth.random_blocks(t, N, K, seed=1)).to(dev)
@@ -31,7 +32,7 @@ with torch.cuda.stream(s):
 tr = trace.cpu().numpy().reshape(-1, 256, 4)[:nl, :148].astype(np.float64)
 t0 = tr[0, :, 0].min()
 tr = (tr - t0) / 1e3
-print(f"static={static} warps={warps} cap={cap} N={N} K={K} B={B}   (us since first CTA start)")
+print(f"l2={l2} static={static} warps={warps} cap={cap} N={N} K={K} B={B}   (us since first CTA start)")
 for i in range(nl):
     a = tr[i]
     print(f"launch {i}: start {a[:,0].min():7.2f}..{a[:,0].max():7.2f}  dep-wait done {a[:,1].min():7.2f}..{a[:,1].max():7.2f}  "
