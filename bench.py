@@ -181,7 +181,7 @@ def run_reference(args, rank, world):
                          "sample": f"{args.steps} passes of the full sweep; oracle port (ggml-cpu has no K-quant case), OpenMP"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -198,6 +198,7 @@ def run_b200(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=dev)
     peaks, peak_kind = measured_peaks()
     hbm_peak = float(peaks["hbm_gbs"])
@@ -228,19 +229,15 @@ def run_b200(args, rank, local_rank, world):
         clocks.start()
         time.sleep(0.3)
 
-    # ---- timed region: exactly K steps, CUDA events on the launching (current) stream
+    # ---- timed region: exactly K steps, CUDA events on the launching (current) stream.  Nothing but the
+    # launches sits between the two events: the kernels are programmatic dependent launches, and an event
+    # record between two of them would serialise what a real caller's stream overlaps.
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    per = {t: [] for t in SWEEP}
     barrier()
     t_wall0 = clocks.mark()
     ev0.record()
     for _ in range(args.steps):
-        for t in SWEEP:
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            ggml.dequantize_out(w_dev[t], t, ROWS, COLS, out_dev[t])
-            b.record()
-            per[t].append((a, b))
+        step()
     ev1.record()
     barrier()
     t_wall1 = clocks.mark()
@@ -250,6 +247,18 @@ def run_b200(args, rank, local_rank, world):
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         ms = float(tm.item())
     value = world * step_bytes * args.steps / (ms * 1e-3) / 1e9
+
+    # ---- per-kernel durations (roofline): the same K steps again, one event pair per launch
+    per = {t: [] for t in SWEEP}
+    for _ in range(args.steps):
+        for t in SWEEP:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            ggml.dequantize_out(w_dev[t], t, ROWS, COLS, out_dev[t])
+            b.record()
+            per[t].append((a, b))
+    barrier()
+    t_wall1 = clocks.mark()
     kern_ms = {t: statistics.mean(a.elapsed_time(b) for a, b in per[t]) for t in SWEEP}
     clk = clocks.stop(t_wall0, t_wall1) if rank == 0 else None
 
@@ -289,7 +298,7 @@ def run_b200(args, rank, local_rank, world):
         e2e_s = float(tm.item())
     e2e_val = world * step_bytes * e2e_steps / e2e_s / 1e9
 
-    launches = args.steps * len(SWEEP)
+    launches = 2 * args.steps * len(SWEEP)
     extras = {}
     if not args.no_extras:
         try:
@@ -317,7 +326,8 @@ def run_b200(args, rank, local_rank, world):
         "roofline": {"kernel": "dequant_tile_kernel<Q4_K, half>", "bound": "hbm", "achieved": q4k_gbs, "peak": hbm_peak,
                      "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
                      "unit": "GB/s", "frac": q4k_gbs / hbm_peak, "traffic": traffic,
-                     "algorithmic_bytes_per_launch": q4k_bytes, "avg_launch_ms": kern_ms[12]},
+                     "algorithmic_bytes_per_launch": q4k_bytes, "avg_launch_ms": kern_ms[12],
+                     "how": "event pair around every launch of a second pass of the K steps (serialised launches)"},
         "per_type_GBps": {synth.NAMES[t]: (in_bytes[t] + out_bytes) / (kern_ms[t] * 1e-3) / 1e9 for t in SWEEP},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": sum(in_bytes.values()),
                 "d2h_bytes_per_step": out_bytes * len(SWEEP), "steps": e2e_steps,
@@ -330,12 +340,31 @@ def run_b200(args, rank, local_rank, world):
         import oracle  # cpu_baseline leg only
         weights = {t: w_host[t].numpy() for t in SWEEP}
         line["cpu_baseline"] = cpu_baseline(weights)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def _claim_stdout():
+    """Route fd 1 to stderr for the whole run (NCCL / torchrun banners) and return a writer on the real stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
+_OUT = None
+
+
+def emit(line: dict) -> None:
+    """The one JSON line, on the real stdout."""
+    _OUT.write(json.dumps(line) + "\n")
+    _OUT.flush()
+
+
 def main():
+    global _OUT
+    _OUT = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -28,7 +28,7 @@ constexpr int kThreads = 256;
 // ---- the tile kernel --------------------------------------------------------------------------
 template <int TYPE, typename OutT>
 __global__ void __launch_bounds__(kThreads)
-dequant_tile_kernel(const uint8_t *__restrict__ W, OutT *__restrict__ out, int64_t nblocks, int w_aligned16) {
+dequant_tile_kernel(const uint8_t *__restrict__ W, OutT *__restrict__ out, int64_t nblocks, int w_aligned16, int static_w) {
     constexpr int QK = BlockTraits<TYPE>::QK, BS = BlockTraits<TYPE>::BS;
     constexpr int TILE_BLOCKS = kTileValues / QK;
     constexpr int TILE_BYTES = TILE_BLOCKS * BS;           // multiple of 16 for every type
@@ -43,17 +43,23 @@ dequant_tile_kernel(const uint8_t *__restrict__ W, OutT *__restrict__ out, int64
     const int nb = (int)min((int64_t)TILE_BLOCKS, nblocks - b0);
     const uint8_t *src = W + b0 * BS;
 
+    // programmatic dependent launch: the first wave of this grid becomes resident under the tail of the previous
+    // kernel; with static weights its tile loads start right away, everything else waits for that kernel
+    ggb_pdl_launch_dependents();
     if (nb == TILE_BLOCKS && w_aligned16) {
         // TMA path: one elected thread arms the mbarrier and issues one bulk copy for the tile.
         if (tid == 0) {
             mbar_init(&bar, 1);
             fence_mbar_init();
             mbar_expect_tx(&bar, TILE_BYTES);
+            if (!static_w) ggb_pdl_wait();
             bulk_g2s_hint(tile, src, TILE_BYTES, &bar, l2_policy_evict_first());
         }
+        ggb_pdl_wait();
         __syncthreads();                                   // barrier object is initialised for everyone
         mbar_wait(&bar, 0);
     } else {
+        ggb_pdl_wait();
         // ragged last tile or a weight pointer that is not 16-byte aligned: cooperative 2-byte copy
         const int nbytes = nb * BS;
         for (int i = 2 * tid; i < nbytes; i += 2 * kThreads)
@@ -116,9 +122,17 @@ int launch_dequant(const void *W, void *out, int64_t nelem, cudaStream_t stream)
         return GGB_E_SHAPE;
     }
     const int aligned = (reinterpret_cast<uintptr_t>(W) & 15) == 0;
-    dequant_tile_kernel<TYPE, OutT><<<(unsigned)ntiles, kThreads, 0, stream>>>(
-        static_cast<const uint8_t *>(W), static_cast<OutT *>(out), nblocks, aligned);
-    GGB_CUDA_TRY(cudaGetLastError());
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)ntiles);
+    cfg.blockDim = dim3(kThreads);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, dequant_tile_kernel<TYPE, OutT>, static_cast<const uint8_t *>(W),
+                                    static_cast<OutT *>(out), nblocks, aligned, ggb_static_weights()));
     return GGB_OK;
 }
 

@@ -45,6 +45,8 @@ struct DeviceInfo {
 };
 // cached per device after the first call (the reference re-queries on every launch, mmq.cu:17-54)
 const DeviceInfo &ggb_device_info();
+// ggb_set_option(GGB_OPT_STATIC_WEIGHTS): weight tensors are never written by work enqueued shortly before
+int ggb_static_weights();
 
 // ---------------------------------------------------------------- small device helpers
 __device__ __forceinline__ float ggb_h2f(uint16_t bits) {
@@ -111,6 +113,13 @@ template <typename T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// ---------------------------------------------------------------- programmatic dependent launch
+// Kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization: their CTAs may become resident
+// while the previous kernel of the stream drains.  ggb_pdl_wait() returns once that kernel has completed and its
+// writes are visible: nothing it may have produced is read, and nothing it may still read is written, before it.
+__device__ __forceinline__ void ggb_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void ggb_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---------------------------------------------------------------- mbarrier + bulk-copy (TMA 1-D) PTX
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {

@@ -57,7 +57,10 @@ struct Params {
     int raw_slot;            // bytes per row in a raw stage
     int w_fast;              // W 16-byte aligned and total bytes % 16 == 0: bulk copies
     int w_lo;                // low 4 bits of W (0 in the fast path)
-    int off_b, off_raw, off_tab, off_bar;
+    int img_plane;           // token atoms (8 tokens) per K-plane of the B image (the full activation matrix's)
+    int ntiles_run;          // cluster-level tiles this launch processes (the rest belongs to a tail launch)
+    int off_b, off_raw, off_tab, off_epi, off_bar;
+    int y_vec;               // Y rows can take 16-byte stores (Y 16-byte aligned, ldy * sizeof(T) % 16 == 0)
 };
 
 // ---------------------------------------------------------------- tcgen05 / descriptor helpers
@@ -190,7 +193,7 @@ mmq_kernel(const Params p, const __grid_constant__ CUtensorMap tmapW) {
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_rbg = (p.n_row_blocks + CL - 1) / CL;          // row-block groups (CL row blocks each; a phantom one is all zeros)
-    const int ntiles = n_rbg * p.n_tok_groups;                // cluster-level tiles
+    const int ntiles = min(n_rbg * p.n_tok_groups, p.ntiles_run);     // cluster-level tiles
     const int ksteps_total = p.nsb * (RAWK / KSTEP);
     const int crank = (CL == 1) ? 0 : (int)(blockIdx.x % CL), cid = blockIdx.x / CL, ncl = gridDim.x / CL;
 
@@ -246,7 +249,7 @@ mmq_kernel(const Params p, const __grid_constant__ CUtensorMap tmapW) {
                     if (lane == 0) {
                         const int ks = sb * (RAWK / KSTEP) + q;
                         // the nb_valid token tiles of a group are adjacent in the image: one contiguous copy
-                        const uint8_t *src = p.Ximg + ((int64_t)ks * (p.Mp >> 3) + (int64_t)tt * (BN >> 3)) * 1024;
+                        const uint8_t *src = p.Ximg + ((int64_t)ks * p.img_plane + (int64_t)tt * (BN >> 3)) * 1024;
                         mbar_expect_tx(&b_full[s], (uint32_t)(nb_valid * B_TILE_BYTES));
                         if (CL == 1) {
                             bulk_g2s_plain(sB + s * B_STAGE_BYTES, src, (uint32_t)(nb_valid * B_TILE_BYTES), &b_full[s]);
@@ -303,21 +306,48 @@ mmq_kernel(const Params p, const __grid_constant__ CUtensorMap tmapW) {
             const int ab = tcount % NACC;
             mbar_wait(&acc_full[ab], (uint32_t)(tcount / NACC) & 1u);
             tc_fence_after();
-            const int64_t wrow = (int64_t)rb * BM + quad * 32 + lane;
             const int64_t tok0 = (int64_t)tg * NB * BN;
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * ACC_COLS);
             constexpr int NCH = (BN + 31) / 32;
+            constexpr int VPT = 16 / (int)sizeof(T);          // values per 16-byte vector
+            constexpr int VPR = BM / VPT;                     // vectors per staged token row (128 weight rows)
+            constexpr int TS = 16 * VPT / 4;                  // tokens per staging pass: an 8 KB buffer (32 for fp16/bf16, 16 for fp32)
+            T *stage = reinterpret_cast<T *>(smem + p.off_epi);               // [TS tokens][128 weight rows]
+            const int et = tid - kFirstEpiWarp * 32;          // 0..127
+            const int64_t row0 = (int64_t)rb * BM;
 #pragma unroll 1
             for (int ch = 0; ch < NCH * nb_valid; ch++) {
                 uint32_t v[32];
                 tmem_ld32(taddr + ch * 32, v);        // NB == 2: the second accumulator follows at column ACC_COLS == BN
                 tmem_ld_wait();
-                if (wrow < p.N) {
+                // The accumulator is weight-row major (one TMEM lane per row): stores straight from it are 64-byte
+                // pieces at a 2 * ldy stride.  Transposed through shared memory, every token row of the tile leaves
+                // as 256 contiguous bytes (fp16) in 16-byte vectors.
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const int64_t tok = tok0 + ch * 32 + j;
-                        if ((NB == 2 || ch * 32 + j < BN) && tok < p.M) Y[tok * p.ldy + wrow] = from_f32<T>(__uint_as_float(v[j]));
+                for (int h = 0; h < 32 / TS; h++) {
+#pragma unroll
+                    for (int j = 0; j < TS; j++) stage[j * BM + quad * 32 + lane] = from_f32<T>(__uint_as_float(v[h * TS + j]));
+                    asm volatile("bar.sync 2, 128;" ::: "memory");
+#pragma unroll
+                    for (int it = 0; it < TS * VPR / 128; it++) {
+                        const int vid = et + it * 128, j = vid / VPR, c = vid % VPR;
+                        const int jt = ch * 32 + h * TS + j;
+                        const int64_t tok = tok0 + jt;
+                        const int64_t r = row0 + c * VPT;
+                        if ((NB == 2 || jt < BN) && tok < p.M && r < p.N) {
+                            const uint4 val = *reinterpret_cast<const uint4 *>(stage + j * BM + c * VPT);
+                            T *dst = Y + tok * p.ldy + r;
+                            if (p.y_vec && r + VPT <= p.N) {
+                                *reinterpret_cast<uint4 *>(dst) = val;
+                            } else {
+                                const T *e = reinterpret_cast<const T *>(&val);
+#pragma unroll
+                                for (int k = 0; k < VPT; k++)
+                                    if (r + k < p.N) dst[k] = e[k];
+                            }
+                        }
                     }
+                    asm volatile("bar.sync 2, 128;" ::: "memory");
                 }
             }
             tc_fence_before();
@@ -449,8 +479,11 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // returns 1 when the configuration does not fit in shared memory (the caller tries the next one)
+// img_plane = token atoms per K-plane of the image (0: this problem's own padded M); tile_limit = cluster-level tiles to
+// run (-1: all)
 template <int TYPE, int BN, int NB, int CL, typename T>
-int launch_gemm(const void *W, const uint8_t *img, void *Y, int64_t M, int64_t K, int64_t N, int64_t ldy, cudaStream_t stream) {
+int launch_gemm(const void *W, const uint8_t *img, void *Y, int64_t M, int64_t K, int64_t N, int64_t ldy, cudaStream_t stream,
+                int img_plane = 0, int tile_limit = -1) {
     constexpr int NSTAGE = nstage_of(NB);
     constexpr int QK = BlockTraits<TYPE>::QK, BS = BlockTraits<TYPE>::BS;
     constexpr int SB_BYTES = RAWK / QK * BS;
@@ -465,7 +498,9 @@ int launch_gemm(const void *W, const uint8_t *img, void *Y, int64_t M, int64_t K
     p.K = (int)K;
     p.row_bytes = (int)(K / QK * BS);
     p.nsb = (int)(padded_k(K) / RAWK);
-    p.Mp = (int)padded_m(M);
+    p.Mp = (int)((M + BN - 1) / BN * BN);
+    p.img_plane = img_plane > 0 ? img_plane : (int)(padded_m(M) >> 3);
+    p.ntiles_run = tile_limit >= 0 ? tile_limit : 0x7fffffff;
     p.n_row_blocks = (int)((N + BM - 1) / BM);
     p.n_tok_tiles = p.Mp / BN;
     p.n_tok_groups = (p.n_tok_tiles + NB - 1) / NB;
@@ -498,7 +533,9 @@ int launch_gemm(const void *W, const uint8_t *img, void *Y, int64_t M, int64_t K
     p.off_raw = p.off_b + NSTAGE * NB * BN * 128;
     p.off_raw = (p.off_raw + 1023) & ~1023;
     p.off_tab = (p.off_raw + NRAW * BM * p.raw_slot + 127) & ~127;
-    p.off_bar = (p.off_tab + (HalfUnpack<TYPE>::HAS ? NRAW * BM * HalfUnpack<TYPE>::NSUB * 4 : 0) + 127) & ~127;
+    p.off_epi = (p.off_tab + (HalfUnpack<TYPE>::HAS ? NRAW * BM * HalfUnpack<TYPE>::NSUB * 4 : 0) + 127) & ~127;
+    p.off_bar = p.off_epi + 8192;
+    p.y_vec = ((reinterpret_cast<uintptr_t>(Y) & 15) == 0) && ((ldy * (int64_t)sizeof(T)) % 16 == 0);
     const int smem = p.off_bar + 256 + 1024;     // + slack so the kernel can align its base to 1024
     if (smem > di.max_smem_optin) {
         if (NB > 1) return 1;
@@ -510,7 +547,9 @@ int launch_gemm(const void *W, const uint8_t *img, void *Y, int64_t M, int64_t K
         GGB_CUDA_TRY(cudaFuncSetAttribute(mmq_kernel<TYPE, BN, NB, CL, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin));
         attr_set[di.dev] = true;
     }
-    const int64_t ntiles = (int64_t)((p.n_row_blocks + CL - 1) / CL) * p.n_tok_groups;       // cluster-level tiles
+    int64_t ntiles = (int64_t)((p.n_row_blocks + CL - 1) / CL) * p.n_tok_groups;             // cluster-level tiles
+    if (ntiles > p.ntiles_run) ntiles = p.ntiles_run;
+    if (ntiles <= 0) return GGB_OK;
     const int64_t max_cl = di.sm_count / CL;
     const int grid = (int)(ntiles < max_cl ? ntiles : max_cl) * CL;
     cudaLaunchConfig_t cfg = {};
@@ -539,9 +578,29 @@ int run_typed(const void *W, const void *X, void *Y, int64_t M, int64_t K, int64
             // enough tokens for two 256-token tiles per unpacked weight stage, and enough tiles to fill the GPU
             if (M > 256 && (g_mmq_cfg & 1) == 0 &&
                 ((N + BM - 1) / BM) * ((padded_m(M) / 256 + 1) / 2) >= ggb_device_info().sm_count) {
-                rc = (g_mmq_cfg & 2) ? launch_gemm<TYPE, 256, 2, 1, T>(W, img, Y, M, K, N, ldy, stream)
-                                     : launch_gemm<TYPE, 256, 2, 2, T>(W, img, Y, M, K, N, ldy, stream);
-                if (rc != 1) return rc;
+                if (g_mmq_cfg & 2) {
+                    rc = launch_gemm<TYPE, 256, 2, 1, T>(W, img, Y, M, K, N, ldy, stream);
+                    if (rc != 1) return rc;
+                } else {
+                    // Wave quantisation: with 74 clusters, the last round of 128 x 512 tiles is often nearly empty (M = 2048:
+                    // 224 cluster tiles = 3 rounds + 2 tiles).  Those last `rem` tiles are a rectangle (the last row blocks of
+                    // the last token group): run them as 128 x 64 tiles in a second launch that fills the GPU for a fraction
+                    // of a round instead.
+                    const int sms = ggb_device_info().sm_count, ncl = sms / 2;
+                    const int n_rbg = (int)(((N + BM - 1) / BM + 1) / 2), n_tg = (int)((padded_m(M) / 256 + 1) / 2);
+                    const int ntiles = n_rbg * n_tg, rem = ntiles % ncl;
+                    const bool tail = (g_mmq_cfg & 4) == 0 && ntiles > ncl && rem > 0 && rem <= n_rbg && rem * 16 <= sms + sms / 4 &&
+                                      (K % 256 == 0 || BlockTraits<TYPE>::QK == 32);
+                    rc = launch_gemm<TYPE, 256, 2, 2, T>(W, img, Y, M, K, N, ldy, stream, 0, tail ? ntiles - rem : -1);
+                    if (rc != 1) {
+                        if (rc != GGB_OK || !tail) return rc;
+                        const int64_t row0 = (int64_t)(n_rbg - rem) * 2 * BM, tok0 = (int64_t)(n_tg - 1) * 512;
+                        const int64_t row_bytes = K / BlockTraits<TYPE>::QK * BlockTraits<TYPE>::BS;
+                        return launch_gemm<TYPE, 64, 1, 1, T>(static_cast<const uint8_t *>(W) + row0 * row_bytes, img + (tok0 >> 3) * 1024,
+                                                              static_cast<T *>(Y) + tok0 * ldy + row0, M - tok0, K, N - row0, ldy, stream,
+                                                              (int)(padded_m(M) >> 3));
+                    }
+                }
             }
             if ((g_mmq_cfg & 2) == 0 && (N + BM - 1) / BM * (padded_m(M) / 256) >= ggb_device_info().sm_count)
                 return launch_gemm<TYPE, 256, 1, 2, T>(W, img, Y, M, K, N, ldy, stream);

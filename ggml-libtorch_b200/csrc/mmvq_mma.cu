@@ -43,18 +43,19 @@ constexpr int kScrWords = 16 * 8;       // per-warp scratch buffer: 16 rows x {s
 // Activation image (workspace and shared memory, same layout):
 //   [0, B * act_stride)             int8 quants, token-major, act_stride = K + 32 (conflict-free 64-bit reads)
 //   [off_d, ...)   float2 per (token pair p, group G): {d8[2p][G], d8[2p+1][G]}, pair stride d_stride2 float2
-//   [off_s, ...)   float2 per (token b, group G): tf32 split {hi, lo} of d8 * sum(q8); token stride s_stride2
+//   [off_s, ...)   float2 per (token b, group G): tf32 split {hi, lo} of d8 * sum(q8); token stride s_stride2.
+//                  Q6_K (s16): per 16-value sub-block instead, of 32 * d8 * sum(q8 of the sub-block)
 struct ActLayout {
     int act_stride, off_d, d_stride2, off_s, s_stride2, total;
 };
-__host__ __device__ inline ActLayout act_layout(int B, int K) {
+__host__ __device__ inline ActLayout act_layout(int B, int K, bool s16) {
     ActLayout L;
     const int ng = K / 32, npairs = (B + 1) / 2;
     L.act_stride = K + 32;
     L.off_d = (B * L.act_stride + 15) & ~15;
     L.d_stride2 = ng + 2;                                   // + 16 B: token pairs land in different banks
     L.off_s = (L.off_d + npairs * L.d_stride2 * 8 + 15) & ~15;
-    L.s_stride2 = ng + 2;
+    L.s_stride2 = (s16 ? 2 * ng : ng) + 2;
     L.total = (L.off_s + B * L.s_stride2 * 8 + 15) & ~15;
     return L;
 }
@@ -116,12 +117,12 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1
 // ------------------------------------------------------------------------------------------------
 // launch 1: the activation image
 // ------------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, bool S16>
 __global__ void __launch_bounds__(256)
 mmvq_act_image_kernel(const T *__restrict__ X, uint8_t *__restrict__ img, int B, int K, int x_vec) {
     pdl_launch_dependents();
     pdl_wait();                                             // X comes from the previous kernel of the stream
-    const ActLayout L = act_layout(B, K);
+    const ActLayout L = act_layout(B, K, S16);
     const int ng = K >> 5;
     const int t4 = threadIdx.x & 3;
     const int gi = blockIdx.x * 64 + (threadIdx.x >> 2);    // group index over 2 * npairs tokens (warp-uniform validity per 8 groups)
@@ -138,12 +139,19 @@ mmvq_act_image_kernel(const T *__restrict__ X, uint8_t *__restrict__ img, int B,
     const Q8Group qg = q8_1_quantize_group<false>(v);
     int sum = __dp4a((int)qg.q_lo, 0x01010101, __dp4a((int)qg.q_hi, 0x01010101, 0));
     sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    const int sum16 = sum;                                   // this lane pair's 16-value half of the group
     sum += __shfl_xor_sync(0xffffffffu, sum, 2);
     if (b < B) *reinterpret_cast<uint2 *>(img + b * L.act_stride + g * 32 + t4 * 8) = make_uint2(qg.q_lo, qg.q_hi);
-    if (t4 == 0) {
-        const float d8 = __half2float(__float2half_rn(qg.d));
-        reinterpret_cast<float *>(img + L.off_d)[((b >> 1) * L.d_stride2 + g) * 2 + (b & 1)] = d8;
-        if (b < B) {
+    const float d8 = __half2float(__float2half_rn(qg.d));
+    if (t4 == 0) reinterpret_cast<float *>(img + L.off_d)[((b >> 1) * L.d_stride2 + g) * 2 + (b & 1)] = d8;
+    if (b < B) {
+        if (S16) {
+            if ((t4 & 1) == 0) {
+                const float s8 = d8 * (float)(32 * sum16);
+                const float hi = __uint_as_float(__float_as_uint(s8) & 0xffffe000u);
+                reinterpret_cast<float2 *>(img + L.off_s)[b * L.s_stride2 + 2 * g + (t4 >> 1)] = make_float2(hi, s8 - hi);
+            }
+        } else if (t4 == 0) {
             const float s8 = d8 * (float)sum;
             const float hi = __uint_as_float(__float_as_uint(s8) & 0xffffe000u);
             reinterpret_cast<float2 *>(img + L.off_s)[b * L.s_stride2 + g] = make_float2(hi, s8 - hi);
@@ -184,6 +192,7 @@ template <int TYPE>
 __device__ __forceinline__ void k45_step(const uint8_t *r0, const uint8_t *r1, const uint8_t *ap, const float2 *dp,
                                          const float2 *sp, int *scr, int q, int t, float (&acc)[4]) {
     constexpr int QS = (TYPE == T_Q4_K) ? 16 : 48;          // offset of the nibbles
+    ap += 8 * t;
     const K4Head h0 = k4_head(r0, t), h1 = k4_head(r1, t);
     // scales: row-major scratch, 8 ints per row ordered {sc[t], sc[t+4]} by t
     *reinterpret_cast<int2 *>(scr + q * 8 + 2 * t) = make_int2(h0.sc_a, h0.sc_b);
@@ -246,6 +255,7 @@ __device__ __forceinline__ void k45_step(const uint8_t *r0, const uint8_t *r1, c
 
 template <> struct MmaOps<T_Q4_K> {
     static constexpr int BS = 144;
+    static constexpr bool S16 = false;
     __device__ __forceinline__ static void step(const uint8_t *r0, const uint8_t *r1, const uint8_t *ap, const float2 *dp,
                                                 const float2 *sp, int *scr, int q, int t, float (&acc)[4]) {
         k45_step<T_Q4_K>(r0, r1, ap, dp, sp, scr, q, t, acc);
@@ -253,9 +263,99 @@ template <> struct MmaOps<T_Q4_K> {
 };
 template <> struct MmaOps<T_Q5_K> {
     static constexpr int BS = 176;
+    static constexpr bool S16 = false;
     __device__ __forceinline__ static void step(const uint8_t *r0, const uint8_t *r1, const uint8_t *ap, const float2 *dp,
                                                 const float2 *sp, int *scr, int q, int t, float (&acc)[4]) {
         k45_step<T_Q5_K>(r0, r1, ap, dp, sp, scr, q, t, acc);
+    }
+};
+
+// ---- Q6_K: ql[128] @0, qh[64] @128, 16 int8 scales @192 (one per 16 values), d @208; 210-byte blocks are only
+// 2-byte aligned.  Value = d * sc * (q6 - 32): the weights go to the MMA as the unsigned q6 (one m16n8k16 per 16-value
+// sub-block), and the -32 becomes  - d * sum_sub sc[row, sub] * (32 * d8 * sum q8)[token, sub]: a 16 x 8 x 16 GEMM per
+// super-block on the tf32 MMA, like the minima of Q4_K.   (dequantize.cuh:230-254, vecdotq.cuh:331-349)
+__device__ __forceinline__ void mma_u8s8_k16(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+    asm("mma.sync.aligned.m16n8k16.row.col.s32.u8.s8.s32 {%0, %1, %2, %3}, {%4, %5}, {%6}, {%7, %7, %7, %7};"
+        : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3])
+        : "r"(a0), "r"(a1), "r"(b0), "r"(0));
+}
+template <bool AL>
+__device__ __forceinline__ uint32_t ldw_a2(const uint8_t *p) {          // 32-bit word at a 2-byte-aligned address
+    if (AL) return *reinterpret_cast<const uint32_t *>(p);
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(p - 2);
+    return __funnelshift_r(w[0], w[1], 16);
+}
+template <int J>
+__device__ __forceinline__ int sbyte_of(uint32_t w) {                   // sign-extended byte J
+    return (int)(int8_t)(w >> (8 * J));
+}
+
+template <bool AL>
+__device__ __forceinline__ void q6_step(const uint8_t *r0, const uint8_t *r1, const uint8_t *ap, const float2 *dp,
+                                        const float2 *sp, int t, float (&acc)[4]) {
+    const uint8_t *rr[2] = {r0, r1};
+    const uint32_t sh_t = 8u * t;
+    float cm[4] = {0.0f, 0.0f, 0.0f, 0.0f}, fs[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int ip = 0; ip < 2; ip++) {                         // the two 128-value halves: sub-blocks 8ip .. 8ip + 7
+        int sc[2][8];
+        uint32_t a_lo[2], a_hi[2];
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            const uint32_t w0 = ldw_a2<AL>(rr[r] + 192 + 8 * ip), w1 = ldw_a2<AL>(rr[r] + 196 + 8 * ip);
+            sc[r][0] = sbyte_of<0>(w0); sc[r][1] = sbyte_of<1>(w0); sc[r][2] = sbyte_of<2>(w0); sc[r][3] = sbyte_of<3>(w0);
+            sc[r][4] = sbyte_of<0>(w1); sc[r][5] = sbyte_of<1>(w1); sc[r][6] = sbyte_of<2>(w1); sc[r][7] = sbyte_of<3>(w1);
+            // tf32 A fragment of this k8 step: columns t and t + 4 = sub-blocks 8ip + t, 8ip + t + 4 (exact: |sc| <= 128)
+            a_lo[r] = __float_as_uint((float)(int)(int8_t)(w0 >> sh_t));
+            a_hi[r] = __float_as_uint((float)(int)(int8_t)(w1 >> sh_t));
+        }
+        {
+            const float2 sa = sp[8 * ip + t], sb = sp[8 * ip + t + 4];
+            mma_tf32(cm, a_lo[0], a_lo[1], a_hi[0], a_hi[1], __float_as_uint(sa.x), __float_as_uint(sb.x));
+            mma_tf32(cm, a_lo[0], a_lo[1], a_hi[0], a_hi[1], __float_as_uint(sa.y), __float_as_uint(sb.y));
+        }
+        // w[row][u][r]: this lane's 4 values (bytes 16u + 4t ..) of sub-block 8ip + 2r + u
+        uint32_t w[2][2][4];
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const uint32_t l0 = ldw_a2<AL>(rr[r] + 64 * ip + 16 * u + 4 * t);
+                const uint32_t l1 = ldw_a2<AL>(rr[r] + 64 * ip + 32 + 16 * u + 4 * t);
+                const uint32_t h = ldw_a2<AL>(rr[r] + 128 + 32 * ip + 16 * u + 4 * t);
+                w[r][u][0] = (l0 & 0x0f0f0f0fu) | ((h << 4) & 0x30303030u);
+                w[r][u][1] = (l1 & 0x0f0f0f0fu) | ((h << 2) & 0x30303030u);
+                w[r][u][2] = ((l0 >> 4) & 0x0f0f0f0fu) | (h & 0x30303030u);
+                w[r][u][3] = ((l1 >> 4) & 0x0f0f0f0fu) | ((h >> 2) & 0x30303030u);
+            }
+#pragma unroll
+        for (int r4 = 0; r4 < 4; r4++) {                     // 32-value group 4ip + r4 = sub-blocks 2 r4, 2 r4 + 1 of this half
+            const uint8_t *a = ap + 16 * (8 * ip + 2 * r4) + 4 * t;
+            const uint32_t ba = *reinterpret_cast<const uint32_t *>(a), bb = *reinterpret_cast<const uint32_t *>(a + 16);
+            int ca[4], cb[4];
+            mma_u8s8_k16(ca, w[0][0][r4], w[1][0][r4], ba);
+            mma_u8s8_k16(cb, w[0][1][r4], w[1][1][r4], bb);
+            const float2 d8 = dp[4 * ip + r4];
+            fs[0] = fmaf(d8.x, __int2float_rn(ca[0] * sc[0][2 * r4] + cb[0] * sc[0][2 * r4 + 1]), fs[0]);
+            fs[1] = fmaf(d8.y, __int2float_rn(ca[1] * sc[0][2 * r4] + cb[1] * sc[0][2 * r4 + 1]), fs[1]);
+            fs[2] = fmaf(d8.x, __int2float_rn(ca[2] * sc[1][2 * r4] + cb[2] * sc[1][2 * r4 + 1]), fs[2]);
+            fs[3] = fmaf(d8.y, __int2float_rn(ca[3] * sc[1][2 * r4] + cb[3] * sc[1][2 * r4 + 1]), fs[3]);
+        }
+    }
+    const float d0 = ggb_h2f(ld_u16(r0 + 208)), d1 = ggb_h2f(ld_u16(r1 + 208));
+    acc[0] += d0 * (fs[0] - cm[0]);
+    acc[1] += d0 * (fs[1] - cm[1]);
+    acc[2] += d1 * (fs[2] - cm[2]);
+    acc[3] += d1 * (fs[3] - cm[3]);
+}
+
+template <> struct MmaOps<T_Q6_K> {
+    static constexpr int BS = 210;
+    static constexpr bool S16 = true;
+    __device__ __forceinline__ static void step(const uint8_t *r0, const uint8_t *r1, const uint8_t *ap, const float2 *dp,
+                                                const float2 *sp, int *, int, int t, float (&acc)[4]) {
+        if ((reinterpret_cast<uintptr_t>(r0) & 2) == 0) q6_step<true>(r0, r1, ap, dp, sp, t, acc);     // warp-uniform
+        else q6_step<false>(r0, r1, ap, dp, sp, t, acc);
     }
 };
 
@@ -267,7 +367,7 @@ __global__ void __launch_bounds__(NW * 32, 1)
 mmvq_mma_kernel(const MmaParams p, const __grid_constant__ CUtensorMap tmapW) {
     using Ops = MmaOps<TYPE>;
     extern __shared__ __align__(128) uint8_t smem[];
-    const ActLayout L = act_layout(p.B, p.K);
+    const ActLayout L = act_layout(p.B, p.K, Ops::S16);
     int *scr_all = reinterpret_cast<int *>(smem + p.off_scr);                   // [NW][2][kScrWords]
     float4 *part = reinterpret_cast<float4 *>(smem + p.off_part);               // [2][NW][32]
     uint8_t *slots = smem + p.off_slots;
@@ -308,8 +408,9 @@ mmvq_mma_kernel(const MmaParams p, const __grid_constant__ CUtensorMap tmapW) {
     auto issue_next = [&]() {                                      // whole warp (lane 0 issues)
         if (lane == 0) {
             // rows past N and bytes past the row end are zero-filled by the TMA unit and count as transferred
+            // (blocks that are not multiples of 16 bytes: the box starts at the 16-byte boundary below the chunk)
             mbar_expect_tx(&full[is_ring], (uint32_t)(kRowsPerGroup * p.slot_row_stride));
-            tma_load_2d_hint(slots + is_ring * p.slot_stride, &tmapW, (is_c * p.slot_row_stride) >> 2,
+            tma_load_2d_hint(slots + is_ring * p.slot_stride, &tmapW, ((is_c * p.cs * Ops::BS) & ~15) >> 2,
                              (int)r_begin + is_rg * kRowsPerGroup, &full[is_ring], pol);
         }
         is_c += S;
@@ -337,7 +438,7 @@ mmvq_mma_kernel(const MmaParams p, const __grid_constant__ CUtensorMap tmapW) {
     T *Y = static_cast<T *>(p.Y);
     const int qc = min(q, p.B - 1);                                // lanes of absent tokens shadow the last one
     const int tc = min(t, (p.B - 1) >> 1);                         // ... and absent token pairs the last pair
-    const uint8_t *act_tok = smem + qc * L.act_stride + 8 * t;
+    const uint8_t *act_tok = smem + qc * L.act_stride;
     const float2 *d_pair = reinterpret_cast<const float2 *>(smem + L.off_d) + tc * L.d_stride2;
     const float2 *s_tok = reinterpret_cast<const float2 *>(smem + L.off_s) + qc * L.s_stride2;
     int *scr = scr_all + warp * (2 * kScrWords);
@@ -351,12 +452,12 @@ mmvq_mma_kernel(const MmaParams p, const __grid_constant__ CUtensorMap tmapW) {
             const int sb0 = c * p.cs;
             const int nsbc = min(p.cs, nsb - sb0);
             mbar_wait(&full[ring], phase);
-            const uint8_t *r0 = slots + ring * p.slot_stride + q * p.slot_row_stride;
+            const uint8_t *r0 = slots + ring * p.slot_stride + q * p.slot_row_stride + ((sb0 * Ops::BS) & 15);
             const uint8_t *r1 = r0 + 8 * p.slot_row_stride;
 #pragma unroll 1
             for (int i = 0; i < nsbc; i++) {
                 const int sb = sb0 + i;
-                Ops::step(r0 + i * Ops::BS, r1 + i * Ops::BS, act_tok + sb * 256, d_pair + sb * 8, s_tok + sb * 8,
+                Ops::step(r0 + i * Ops::BS, r1 + i * Ops::BS, act_tok + sb * 256, d_pair + sb * 8, s_tok + sb * (Ops::S16 ? 16 : 8),
                           scr + (step_no & 1) * kScrWords, q, t, acc);
                 step_no++;
             }
@@ -415,10 +516,11 @@ namespace {
 template <int TYPE>
 bool plan(MmaParams &p, int &smem, int NW, int cs, int B, int K, int max_smem) {
     using Ops = MmaOps<TYPE>;
-    const ActLayout L = act_layout(B, K);
+    const ActLayout L = act_layout(B, K, Ops::S16);
     p.cs = cs < p.nsb ? cs : p.nsb;
-    const int rs = p.cs * Ops::BS;
-    if (rs % 16 != 0 || rs > 1024) return false;               // chunk starts 16-byte aligned; TMA box <= 256 uint32
+    // TMA box: the chunk's bytes, from the 16-byte boundary at or below its start (Q6_K: 210-byte blocks)
+    const int rs = (Ops::BS % 16 == 0) ? p.cs * Ops::BS : ((p.cs * Ops::BS + 14 + 15) & ~15);
+    if (rs > 1024) return false;                               // TMA box <= 256 uint32 elements
     p.nchunks = (p.nsb + p.cs - 1) / p.cs;
     int sl = 0;
     while ((2 << sl) <= p.nchunks && (2 << sl) <= NW) sl++;      // S = largest power of two <= min(nchunks, NW)
@@ -510,7 +612,7 @@ int launch(const void *W, const void *X, void *Y, int64_t B, int64_t K, int64_t 
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         const int x_vec = (reinterpret_cast<uintptr_t>(X) & 15) == 0;
-        GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmvq_act_image_kernel<T>, static_cast<const T *>(X), static_cast<uint8_t *>(ws),
+        GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmvq_act_image_kernel<T, Ops::S16>, static_cast<const T *>(X), static_cast<uint8_t *>(ws),
                                         (int)B, (int)K, x_vec));
     }
     return nw == 16 ? launch_gemv<TYPE, T, 16>(p, smem, tmap, stream) : launch_gemv<TYPE, T, 8>(p, smem, tmap, stream);
@@ -527,7 +629,7 @@ int dispatch_dtype(const void *W, const void *X, void *Y, int dt, int64_t B, int
 }
 
 bool mma_applies(int type, int64_t B, int64_t K) {
-    return (type == T_Q4_K || type == T_Q5_K) && B >= g_min_batch && B <= 8 && K % 256 == 0 && K <= (1 << 16);
+    return (type == T_Q4_K || type == T_Q5_K || type == T_Q6_K) && B >= g_min_batch && B <= 8 && K % 256 == 0 && K <= (1 << 16);
 }
 
 }  // namespace
@@ -541,17 +643,29 @@ void ggb_mmvq_mma_tune(int cs, int s_log2_plus1, int min_batch) {
 // workspace for the activation image (0 when this path does not apply)
 int64_t ggb_mmvq_mma_workspace_bytes(int type, int64_t B, int64_t K) {
     if (!mma_applies(type, B, K)) return 0;
-    return act_layout((int)B, (int)K).total;
+    return act_layout((int)B, (int)K, type == T_Q6_K).total;
 }
 
 // returns GGB_OK / a negative status, or 1 when this path does not apply (the caller tries mmvq_sb.cu, then mmvq.cu)
 int ggb_mmvq_mma_impl(const void *W, const void *X, void *Y, int type, int xy_dtype, int64_t B, int64_t K, int64_t N,
                       void *ws, int64_t ws_bytes, cudaStream_t stream) {
     if (!mma_applies(type, B, K) || (reinterpret_cast<uintptr_t>(W) & 15)) return 1;
-    if (!ws || (reinterpret_cast<uintptr_t>(ws) & 15) || ws_bytes < act_layout((int)B, (int)K).total) return 1;
+    if (!ws || (reinterpret_cast<uintptr_t>(ws) & 15) || ws_bytes < act_layout((int)B, (int)K, type == T_Q6_K).total) return 1;
+    int rc;
     switch (type) {
-        case T_Q4_K: return dispatch_dtype<T_Q4_K>(W, X, Y, xy_dtype, B, K, N, ws, stream);
-        case T_Q5_K: return dispatch_dtype<T_Q5_K>(W, X, Y, xy_dtype, B, K, N, ws, stream);
+        case T_Q4_K: rc = dispatch_dtype<T_Q4_K>(W, X, Y, xy_dtype, B, K, N, ws, stream); break;
+        case T_Q5_K: rc = dispatch_dtype<T_Q5_K>(W, X, Y, xy_dtype, B, K, N, ws, stream); break;
+        case T_Q6_K: rc = dispatch_dtype<T_Q6_K>(W, X, Y, xy_dtype, B, K, N, ws, stream); break;
         default: return 1;
     }
+    if (rc != 1 || B < 2 * g_min_batch) return rc;
+    // the B x K activation image does not fit in shared memory next to a useful ring (very long rows): two passes
+    // over the weights with half the batch each still beat the dp4a kernels, which would split the batch as well.
+    // The second pass's image kernel waits for the first pass's GEMV (stream order), so both can share `ws`.
+    const int64_t b1 = B / 2;
+    const size_t esz = xy_dtype == GGB_F32 ? 4 : 2;
+    rc = ggb_mmvq_mma_impl(W, X, Y, type, xy_dtype, b1, K, N, ws, ws_bytes, stream);
+    if (rc != GGB_OK) return rc;
+    return ggb_mmvq_mma_impl(W, static_cast<const uint8_t *>(X) + b1 * K * esz, static_cast<uint8_t *>(Y) + b1 * N * esz, type,
+                             xy_dtype, B - b1, K, N, ws, ws_bytes, stream);
 }

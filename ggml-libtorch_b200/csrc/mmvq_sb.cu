@@ -723,6 +723,7 @@ int dispatch_dtype(const void *W, const void *X, void *Y, int dt, int64_t B, int
 
 void ggb_mmvq_sb_set_static_weights(int on) { g_pdl_prefetch = on ? 1 : 0; }
 int ggb_mmvq_static_weights() { return g_pdl_prefetch; }
+int ggb_static_weights() { return g_pdl_prefetch; }
 int ggb_mmvq_l2_prefetch_mb() { return g_l2_prefetch_mb; }
 extern "C" void ggb_debug_mmvq_trace(void *device_buffer) {      // debug only: 4 * 256 u64 per launch, not in the header
     g_trace = static_cast<unsigned long long *>(device_buffer);
