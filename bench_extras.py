@@ -119,30 +119,36 @@ def tp_mlp_section(ggml, synth, dev, rank, world, peaks, peak_kind):
     if I % world or H % world:
         return {"skipped": f"70B MLP does not divide by tp={world}"}, 0
 
-    def shard(t, n_total, k, seed):
+    def shard(t, n_total, k, seed, fused):
         n_local = n_total // world
         w = torch.from_numpy(synth.random_blocks(t, n_local, k, seed=seed + 1000 * rank)).to(dev)
-        return ColumnParallelQuantLinear(w, t, n_total, rank, world)
+        return ColumnParallelQuantLinear(w, t, n_total, rank, world, fused_gather=fused)
 
-    mlp = QuantMLP(shard(12, I, H, 1), shard(12, I, H, 2), shard(14, H, I, 3))
+    variants = [("nccl all-gather", False)] + ([("fused peer stores + barrier (ggb_mmvq_gather)", True)] if world > 1 else [])
+    mlps = {}
+    for name, fused in variants:
+        mlps[name] = QuantMLP(shard(12, I, H, 1, fused), shard(12, I, H, 2, fused), shard(14, H, I, 3, fused))
+    mlp = mlps[variants[0][0]]
     layer_bytes = sum(l.W.numel() for l in (mlp.gate, mlp.up, mlp.down)) * world
     out = {"unit": "us per MLP block (device time, max over ranks)", "tp": world,
-           "layer": "Llama-3-70B MLP: gate/up [28672, 8192] Q4_K, down [8192, 28672] Q6_K, N-sharded, all-gather per projection",
+           "layer": "Llama-3-70B MLP: gate/up [28672, 8192] Q4_K, down [8192, 28672] Q6_K, N-sharded, one exchange per projection",
            "weight_bytes_total": layer_bytes, "cases": []}
     launches = 0
-    for M in (1, 8, 512):
+    for name, fused in variants:
+      mlp = mlps[name]
+      for M in ((1, 8) if fused else (1, 8, 512)):
         x = torch.randn(M, H, dtype=torch.float16, device=dev)
         reps = 8 if M <= 8 else 2
         how = "cuda-graph replay"
         try:
-            # one graph = `reps` MLP blocks (3 matmuls + 3 all-gathers each): host launch cost out of the picture
+            # one graph = `reps` MLP blocks (3 matmuls + 3 exchanges each): host launch cost out of the picture
             def run():
                 for _ in range(reps):
                     mlp(x)
             if world > 1:
                 dist.barrier()
             ms = _time_graph(run, iters=5) / reps
-        except Exception as e:                       # capture of the collective not possible here: eager timing
+        except Exception as e:                       # capture of the exchange not possible here: eager timing
             how = f"eager ({type(e).__name__})"
             torch.cuda.synchronize()
             for _ in range(3):
@@ -163,7 +169,7 @@ def tp_mlp_section(ggml, synth, dev, rank, world, peaks, peak_kind):
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
             ms = float(tm.item())
         launches += (iters + 3) * 3
-        case = {"M": M, "us": ms * 1e3, "timing": how}
+        case = {"M": M, "exchange": name if world > 1 else "none (tp=1)", "us": ms * 1e3, "timing": how}
         if M <= 8:
             case["weight_GBps_aggregate"] = layer_bytes / (ms * 1e-3) / 1e9
             case["frac_of_hbm_peak_per_gpu"] = layer_bytes / world / (ms * 1e-3) / 1e9 / float(peaks["hbm_gbs"])

@@ -22,6 +22,10 @@ void ggb_mmvq_sb_tune(int warps, int smem_cap_kb);
 void ggb_mmq_tune(int nb);
 void ggb_mmvq_sb_set_l2_prefetch(int mb);
 void ggb_mmvq_mma_tune(int cs, int s_log2_plus1, int min_batch);
+int ggb_mmvq_mma_impl(const void *W, const void *X, void *Y, int type, int xy_dtype, int64_t B, int64_t K, int64_t N,
+                      void *ws, int64_t ws_bytes, cudaStream_t stream);
+int ggb_mmvq_sb_impl(const void *W, const void *X, void *Y, int type, int xy_dtype, int64_t B, int64_t K, int64_t N,
+                     cudaStream_t stream);
 
 // ---------------------------------------------------------------- errors
 static thread_local char g_err[512] = "";
@@ -83,6 +87,10 @@ static bool check_dtype(const char *fn, int dt) {
     }
     return true;
 }
+
+// ---------------------------------------------------------------- gather target (see GgbYOut, ggb_common.cuh)
+static thread_local const GgbYOut *g_yout = nullptr;
+const GgbYOut *ggb_current_yout() { return g_yout; }
 
 extern "C" {
 
@@ -190,6 +198,49 @@ static int check_matmul(const char *fn, const void *W, const void *X, const void
         return GGB_E_ARG;
     }
     return GGB_OK;
+}
+
+int ggb_mmvq_gather(const void *W, const void *X, int type, int xy_dtype, int64_t B, int64_t K, int64_t N,
+                    void *const *y_peers, int n_peers, int64_t ldy, int64_t col_offset, void *ws, int64_t ws_bytes,
+                    void *stream) {
+    g_err[0] = 0;
+    if (!y_peers || n_peers < 1 || n_peers > 8 || ldy < col_offset + N || col_offset < 0) {
+        ggb_set_error("ggb_mmvq_gather: need 1..8 output buffers and col_offset + N <= ldy");
+        return GGB_E_ARG;
+    }
+    for (int i = 0; i < n_peers; i++)
+        if (!y_peers[i] || (reinterpret_cast<uintptr_t>(y_peers[i]) & 3)) {
+            ggb_set_error("ggb_mmvq_gather: output buffer %d is null or not 4-byte aligned", i);
+            return GGB_E_ARG;
+        }
+    const int rc0 = check_matmul("ggb_mmvq_gather", W, X, y_peers[0], type, xy_dtype, B, K, N);
+    if (rc0 < 0) return rc0;
+    if (rc0 > 0) return GGB_OK;
+    if (B > 8) {
+        ggb_set_error("ggb_mmvq_gather: batch %lld > 8", (long long)B);
+        return GGB_E_SHAPE;
+    }
+    if (ggb_mmvq_workspace_bytes(type, B, K, N) > ws_bytes || (ws_bytes > 0 && !ws)) {
+        ggb_set_error("ggb_mmvq_gather: workspace too small (%lld < %lld)", (long long)ws_bytes,
+                      (long long)ggb_mmvq_workspace_bytes(type, B, K, N));
+        return GGB_E_ARG;
+    }
+    GgbYOut y = {};
+    for (int i = 0; i < n_peers; i++) y.base[i] = y_peers[i];
+    y.n = n_peers;
+    y.ld = ldy;
+    y.col0 = col_offset;
+    g_yout = &y;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = ggb_mmvq_mma_impl(W, X, nullptr, type, xy_dtype, B, K, N, ws, ws_bytes, st);
+    if (rc == 1) rc = ggb_mmvq_sb_impl(W, X, nullptr, type, xy_dtype, B, K, N, st);
+    g_yout = nullptr;
+    if (rc == 1) {
+        ggb_set_error("ggb_mmvq_gather: type %d with B=%lld, K=%lld is not on the fused path (use ggb_mmvq + an all-gather)",
+                      type, (long long)B, (long long)K);
+        return GGB_E_SHAPE;
+    }
+    return rc;
 }
 
 int64_t ggb_mmvq_workspace_bytes(int type, int64_t B, int64_t K, int64_t N) {

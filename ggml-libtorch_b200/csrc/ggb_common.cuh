@@ -114,6 +114,38 @@ template <> __device__ __forceinline__ float from_f32<float>(float v) { return v
 template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
+// ---------------------------------------------------------------- output target of the MMVQ kernels
+// Y[tok][col0 + row] with leading dimension ld, replicated into `n` buffers: n = 1 is the plain op; n = tp with peer
+// pointers (NVLink P2P mappings of a symmetric buffer) makes the kernel's epilogue the all-gather of a column-parallel
+// layer (ggb_mmvq_gather): every rank writes its slice straight into every rank's copy of the full output.
+struct GgbYOut {
+    void *base[8];
+    int n;
+    long long ld, col0;
+};
+// thread-local target installed by ggb_mmvq_gather for the duration of its call (nullptr: the plain Y argument)
+const GgbYOut *ggb_current_yout();
+inline GgbYOut ggb_make_yout(void *Y, long long N) {
+    if (const GgbYOut *g = ggb_current_yout()) return *g;
+    GgbYOut y = {};
+    y.base[0] = Y;
+    y.n = 1;
+    y.ld = N;
+    y.col0 = 0;
+    return y;
+}
+#ifdef __CUDACC__
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <typename T>
+__device__ __forceinline__ void ggb_yout_store(const GgbYOut &y, long long tok, long long row, float v) {
+    const T h = from_f32<T>(v);
+    const long long idx = tok * y.ld + y.col0 + row;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        if (i < y.n) static_cast<T *>(y.base[i])[idx] = h;
+}
+#endif
+
 // ---------------------------------------------------------------- programmatic dependent launch
 // Kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization: their CTAs may become resident
 // while the previous kernel of the stream drains.  ggb_pdl_wait() returns once that kernel has completed and its

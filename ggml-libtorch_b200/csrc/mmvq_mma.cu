@@ -62,7 +62,7 @@ __host__ __device__ inline ActLayout act_layout(int B, int K, bool s16) {
 
 struct MmaParams {
     const uint8_t *act_img;  // workspace: the activation image written by mmvq_act_image_kernel
-    void *Y;
+    GgbYOut yo;
     int64_t N;
     int K, B;
     int nsb;               // super-blocks per row
@@ -435,7 +435,6 @@ mmvq_mma_kernel(const MmaParams p, const __grid_constant__ CUtensorMap tmapW) {
     if (p.trace && tid == 0) p.trace[blockIdx.x * 4 + 2] = gtime();
 
     // ===================== row groups of 16, K split over the team =====================
-    T *Y = static_cast<T *>(p.Y);
     const int qc = min(q, p.B - 1);                                // lanes of absent tokens shadow the last one
     const int tc = min(t, (p.B - 1) >> 1);                         // ... and absent token pairs the last pair
     const uint8_t *act_tok = smem + qc * L.act_stride;
@@ -487,12 +486,12 @@ mmvq_mma_kernel(const MmaParams p, const __grid_constant__ CUtensorMap tmapW) {
             const int lr = rg * kRowsPerGroup + q;
             const int tok = 2 * t;
             if (lr < nrows) {
-                if (tok < p.B) Y[(int64_t)tok * p.N + r_begin + lr] = from_f32<T>(acc[0]);
-                if (tok + 1 < p.B) Y[(int64_t)(tok + 1) * p.N + r_begin + lr] = from_f32<T>(acc[1]);
+                if (tok < p.B) ggb_yout_store<T>(p.yo, tok, r_begin + lr, acc[0]);
+                if (tok + 1 < p.B) ggb_yout_store<T>(p.yo, tok + 1, r_begin + lr, acc[1]);
             }
             if (lr + 8 < nrows) {
-                if (tok < p.B) Y[(int64_t)tok * p.N + r_begin + lr + 8] = from_f32<T>(acc[2]);
-                if (tok + 1 < p.B) Y[(int64_t)(tok + 1) * p.N + r_begin + lr + 8] = from_f32<T>(acc[3]);
+                if (tok < p.B) ggb_yout_store<T>(p.yo, tok, r_begin + lr + 8, acc[2]);
+                if (tok + 1 < p.B) ggb_yout_store<T>(p.yo, tok + 1, r_begin + lr + 8, acc[3]);
             }
         }
     }
@@ -575,7 +574,7 @@ int launch(const void *W, const void *X, void *Y, int64_t B, int64_t K, int64_t 
     const DeviceInfo &di = ggb_device_info();
     MmaParams p;
     p.act_img = static_cast<const uint8_t *>(ws);
-    p.Y = Y;
+    p.yo = ggb_make_yout(Y, N);
     p.N = N;
     p.K = (int)K;
     p.B = (int)B;
@@ -629,7 +628,10 @@ int dispatch_dtype(const void *W, const void *X, void *Y, int dt, int64_t B, int
 }
 
 bool mma_applies(int type, int64_t B, int64_t K) {
-    return (type == T_Q4_K || type == T_Q5_K || type == T_Q6_K) && B >= g_min_batch && B <= 8 && K % 256 == 0 && K <= (1 << 16);
+    // measured crossover with the dp4a kernel (Llama-8B shapes): batch 3 for K = 4096, batch 2 for the long rows, where
+    // the dp4a kernel's per-CTA activation quantization (3.3 us at K = 14336) costs more than the image kernel's launch
+    const int64_t min_b = (g_min_batch == 3 && K > 8192) ? 2 : g_min_batch;
+    return (type == T_Q4_K || type == T_Q5_K || type == T_Q6_K) && B >= min_b && B <= 8 && K % 256 == 0 && K <= (1 << 16);
 }
 
 }  // namespace
@@ -658,7 +660,7 @@ int ggb_mmvq_mma_impl(const void *W, const void *X, void *Y, int type, int xy_dt
         case T_Q6_K: rc = dispatch_dtype<T_Q6_K>(W, X, Y, xy_dtype, B, K, N, ws, stream); break;
         default: return 1;
     }
-    if (rc != 1 || B < 2 * g_min_batch) return rc;
+    if (rc != 1 || B < 6 || ggb_current_yout()) return rc;
     // the B x K activation image does not fit in shared memory next to a useful ring (very long rows): two passes
     // over the weights with half the batch each still beat the dp4a kernels, which would split the batch as well.
     // The second pass's image kernel waits for the first pass's GEMV (stream order), so both can share `ws`.

@@ -36,7 +36,7 @@ constexpr int kBatchBlock = 4;          // batch rows processed per pass over an
 struct SbParams {
     const uint8_t *W;
     const void *X;
-    void *Y;
+    GgbYOut yo;
     int64_t N;
     int K;
     int nsb;             // super-blocks per row
@@ -540,7 +540,6 @@ mmvq_sb_kernel(const SbParams p) {
     if (p.trace && tid == 0) p.trace[blockIdx.x * 4 + 2] = gtime();
 
     // ===================== one slot = this warp's next row group x chunk =====================
-    T *Y = static_cast<T *>(p.Y);
     const int lpp = p.lpp;
     const int pair = lane / lpp, sbl = lane - pair * lpp;          // row pair inside the slot, lane inside the pair
     int ring = ring_base;
@@ -585,7 +584,7 @@ mmvq_sb_kernel(const SbParams p) {
 #pragma unroll
                 for (int m = 8; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
                 const int lr = lr0 + (up ? 1 : 0);
-                if ((lane & 15) == 0 && lr < nrows) Y[(int64_t)b * p.N + r_begin + lr] = from_f32<T>(v);
+                if ((lane & 15) == 0 && lr < nrows) ggb_yout_store<T>(p.yo, b, r_begin + lr, v);
             }
         } else {
 #pragma unroll
@@ -594,7 +593,7 @@ mmvq_sb_kernel(const SbParams p) {
                 for (int b = 0; b < B; b++) {
                     float v = acc[r][b];
                     for (int m = lpp >> 1; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
-                    if (sbl == 0 && lr0 + r < nrows) Y[(int64_t)b * p.N + r_begin + lr0 + r] = from_f32<T>(v);
+                    if (sbl == 0 && lr0 + r < nrows) ggb_yout_store<T>(p.yo, b, r_begin + lr0 + r, v);
                 }
             }
         }
@@ -625,7 +624,7 @@ int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, cudaStre
     SbParams p;
     p.W = static_cast<const uint8_t *>(W);
     p.X = X;
-    p.Y = Y;
+    p.yo = ggb_make_yout(Y, N);
     p.N = N;
     p.K = (int)K;
     p.nsb = (int)(K / 256);

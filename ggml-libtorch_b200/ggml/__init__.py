@@ -22,7 +22,7 @@ from ._capi import (GGB_BF16, GGB_F16, GGB_F32, GGB_OPT_STATIC_WEIGHTS, GGB_Q8_1
 __all__ = [
     "ggml_dequantize", "ggml_mul_mat_vec_a8", "ggml_mul_mat_a8", "ggml_quantize_q8_1",
     "dequantize_out", "mul_mat_vec_a8_out", "mul_mat_a8_out", "mmq_workspace_bytes", "mmvq_workspace_bytes",
-    "set_option", "GGB_OPT_STATIC_WEIGHTS",
+    "set_option", "GGB_OPT_STATIC_WEIGHTS", "mul_mat_vec_a8_gather",
     "block_elems", "block_bytes", "SUPPORTED_TYPES", "MMVQ_MAX_BATCH",
 ]
 
@@ -138,6 +138,28 @@ def mul_mat_vec_a8_out(W: torch.Tensor, X: torch.Tensor, quant_type: int, row: i
                            ws.numel() * ws.element_size() if ws is not None else 0, _stream(W))
     _capi.check(rc, what)
     return out
+
+
+def mul_mat_vec_a8_gather(W: torch.Tensor, X: torch.Tensor, quant_type: int, row: int, peer_ptrs, ldy: int,
+                          col_offset: int, ws: torch.Tensor | None = None) -> None:
+    """MMVQ of this rank's row slice with the column-parallel all-gather fused into the epilogue (ggb_mmvq_gather):
+    results go to `peer_ptrs[i] + (tok * ldy + col_offset + r) * sizeof(X.dtype)` for every i.  `peer_ptrs` are the
+    device pointers of one symmetric [B, ldy] buffer as mapped on every rank (torch symmetric memory `buffer_ptrs`).
+    The caller runs a cross-rank barrier on the stream before reading the buffer.  Raises ValueError for shapes / types
+    that are not on the fused path."""
+    _check_x(X, W, "ggml_mul_mat_vec_a8")
+    B, K = X.shape
+    _check_w(W, quant_type, row, K, "ggml_mul_mat_vec_a8")
+    import ctypes
+    need = mmvq_workspace_bytes(quant_type, B, K, row)
+    if need and (ws is None or ws.numel() * ws.element_size() < need):
+        ws = torch.empty(need, dtype=torch.uint8, device=W.device)
+    arr = (ctypes.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+    with torch.cuda.device(W.device):
+        rc = _lib.ggb_mmvq_gather(W.data_ptr(), X.data_ptr(), int(quant_type), _DT[X.dtype], B, K, row, arr, len(peer_ptrs),
+                                  int(ldy), int(col_offset), ws.data_ptr() if ws is not None else None,
+                                  ws.numel() * ws.element_size() if ws is not None else 0, _stream(W))
+    _capi.check(rc, "ggml_mul_mat_vec_a8 (gather)")
 
 
 def mmq_workspace_bytes(quant_type: int, M: int, K: int, N: int) -> int:

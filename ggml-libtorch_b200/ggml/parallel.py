@@ -10,6 +10,12 @@ single-GPU result bit for bit.
 
 One process per GPU; `group` is a torch.distributed process group (NCCL on GPUs; the gloo CPU tests
 inject a CPU matmul through `matmul_fn`).
+
+`fused_gather=True` (decode batches, K-quants): the exchange moves INTO the MMVQ kernel.  The full output lives in
+a symmetric buffer (torch symmetric memory: the same allocation mapped into every rank over NVLink); each rank's
+kernel stores its slice straight into every rank's copy (`ggb_mmvq_gather`), and one device-side barrier on the
+stream replaces the NCCL all-gather (whose launch + protocol latency is several times the 114 KB .. 14 KB it moves
+at decode).  Two buffers alternate, so a result stays valid until the second-next call of the layer.
 """
 from __future__ import annotations
 
@@ -49,7 +55,8 @@ class ColumnParallelQuantLinear:
 
     def __init__(self, W_shard: torch.Tensor, quant_type: int, n_total: int, rank: int, world: int,
                  group: Optional[dist.ProcessGroup] = None,
-                 matmul_fn: Callable[[torch.Tensor, torch.Tensor, int, int], torch.Tensor] = _default_matmul):
+                 matmul_fn: Callable[[torch.Tensor, torch.Tensor, int, int], torch.Tensor] = _default_matmul,
+                 fused_gather: bool = False):
         lo, hi = shard_bounds(n_total, rank, world)
         if W_shard.shape[0] != hi - lo:
             raise ValueError(f"shard has {W_shard.shape[0]} rows, expected {hi - lo}")
@@ -58,12 +65,51 @@ class ColumnParallelQuantLinear:
         self.n_total, self.n_local = n_total, hi - lo
         self.rank, self.world, self.group = rank, world, group
         self.matmul_fn = matmul_fn
+        self.fused_gather = bool(fused_gather) and world > 1
+        self._symm = {}          # dtype -> [(buffer, handle, peer pointers)] x 2
+        self._calls = 0
+        self._ws = None
+
+    def _symm_buffers(self, dtype: torch.dtype, device: torch.device):
+        """Two symmetric [MMVQ_MAX_BATCH, N] buffers per dtype (collective on first use: every rank calls it)."""
+        if dtype not in self._symm:
+            import torch.distributed._symmetric_memory as symm_mem
+            from . import MMVQ_MAX_BATCH
+            group = self.group if self.group is not None else dist.group.WORLD
+            bufs = []
+            for _ in range(2):
+                buf = symm_mem.empty((MMVQ_MAX_BATCH, self.n_total), dtype=dtype, device=device)
+                hdl = symm_mem.rendezvous(buf, group)
+                bufs.append((buf, hdl, [int(p) for p in hdl.buffer_ptrs]))
+            self._symm[dtype] = bufs
+        return self._symm[dtype]
+
+    def _forward_fused(self, X: torch.Tensor) -> Optional[torch.Tensor]:
+        from . import mmvq_workspace_bytes, mul_mat_vec_a8_gather
+        M, K = X.shape
+        buf, hdl, ptrs = self._symm_buffers(X.dtype, X.device)[self._calls & 1]
+        need = mmvq_workspace_bytes(self.quant_type, M, K, self.n_local)
+        if need and (self._ws is None or self._ws.numel() < need):
+            self._ws = torch.empty(need, dtype=torch.uint8, device=X.device)
+        try:
+            mul_mat_vec_a8_gather(self.W, X, self.quant_type, self.n_local, ptrs, self.n_total, self.rank * self.n_local,
+                                  self._ws)
+        except ValueError:
+            self.fused_gather = False        # this type / shape is not on the fused path (same verdict on every rank)
+            return None
+        self._calls += 1
+        hdl.barrier(channel=0)               # every rank's slice has landed in this rank's copy
+        return buf[:M]
 
     def local(self, X: torch.Tensor) -> torch.Tensor:
         """This rank's output slice Y[:, lo:hi] (no communication)."""
         return self.matmul_fn(self.W, X, self.quant_type, self.n_local)
 
     def forward(self, X: torch.Tensor) -> torch.Tensor:
+        if self.fused_gather and X.dim() == 2 and X.shape[0] <= 8:
+            y = self._forward_fused(X)
+            if y is not None:
+                return y
         y_local = self.local(X)
         if self.world == 1:
             return y_local

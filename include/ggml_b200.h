@@ -104,6 +104,20 @@ int         ggb_mmvq(const void *W, const void *X, void *Y, int type, int xy_dty
                      int64_t B, int64_t K, int64_t N, void *ws, int64_t ws_bytes, void *stream);
 
 /*
+ * MMVQ with the all-gather of a column-parallel layer fused into its epilogue (no reference counterpart: the reference is
+ * single-GPU).  Same computation as ggb_mmvq on this rank's row slice W [N, K/QK*block_bytes], but
+ * every result is stored to y_peers[i][tok * ldy + col_offset + row] for i < n_peers: the caller passes the base pointers
+ * of one symmetric buffer [B, ldy] as mapped on every rank of the tensor-parallel group (NVLink peer mappings; its own
+ * copy included), ldy = N_total and col_offset = rank * N, so each rank writes its slice into every rank's copy of the
+ * full output.  The caller orders the exchange with a cross-rank barrier on the stream before the result is read.
+ * Types Q4_K / Q5_K / Q6_K with K % 256 == 0 (Q6_K: K % 2048 == 0), 1 <= B <= 8; anything else returns GGB_E_SHAPE and
+ * the caller uses ggb_mmvq + an all-gather.  Workspace: ggb_mmvq_workspace_bytes.
+ */
+int         ggb_mmvq_gather(const void *W, const void *X, int type, int xy_dtype, int64_t B, int64_t K, int64_t N,
+                            void *const *y_peers, int n_peers, int64_t ldy, int64_t col_offset,
+                            void *ws, int64_t ws_bytes, void *stream);
+
+/*
  * MMQ: Y[M, N] (row stride ldy elements) = q8_1_mmq(X[M, K]) . W[N, K]^T.
  * Replaces ggml_mul_mat_a8 (ggml/mmq.cu:180-255): quantize_mmq_q8_1_cuda + mul_mat_q
  * (ggml/mmq.cuh:1917-2031).  `ws` must hold ggb_mmq_workspace_bytes(...) bytes (the quantized

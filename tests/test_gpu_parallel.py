@@ -54,6 +54,15 @@ def _worker(rank, world, port, out_dir):
             x = _inputs(M).to(dev)
             res[f"gate{M}"] = mlp.gate(x).float().cpu().numpy()
             res[f"mlp{M}"] = mlp(x).float().cpu().numpy()
+        # the same layers with the all-gather fused into the MMVQ epilogue (peer stores into a symmetric buffer)
+        mkf = lambda w, tt, n: ColumnParallelQuantLinear(shard_rows(w, rank, world).to(dev), tt, n, rank, world, fused_gather=True)
+        fmlp = QuantMLP(mkf(wg, oracle.Q4_K, INTER), mkf(wu, oracle.Q4_K, INTER), mkf(wd, oracle.Q6_K, HIDDEN))
+        for M in BATCHES:
+            x = _inputs(M).to(dev)
+            for rep in range(3):                     # alternating buffers, back-to-back calls
+                y = fmlp(x)
+            res[f"fused{M}"] = y.float().cpu().numpy()
+        res["fused_active"] = np.array([int(fmlp.gate.fused_gather), int(fmlp.down.fused_gather)])
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), **res)
     finally:
         dist.destroy_process_group()
@@ -80,3 +89,5 @@ def test_column_parallel_world2_nccl(tmp_path):
         for r in (r0, r1):
             assert np.array_equal(r[f"gate{M}"], want_gate), f"gate M={M}: sharded != single-GPU"
             assert np.array_equal(r[f"mlp{M}"], want_mlp), f"mlp M={M}: sharded != single-GPU"
+            assert np.array_equal(r[f"fused{M}"], want_mlp), f"mlp M={M}: fused gather != single-GPU"
+    assert r0["fused_active"].tolist() == [1, 1], "the fused path fell back to NCCL"
