@@ -179,6 +179,34 @@ def tp_mlp_section(ggml, synth, dev, rank, world, peaks, peak_kind):
     return out, launches
 
 
+def config0_section(ggml, synth, dev, peaks, peak_kind):
+    """BASELINE configs[0] on the GPU: Q4_0 and Q8_0 dequantize of a 4096x4096 weight to fp32 (the reference CPU op's
+    case and dtype; its own single-thread time is in cpu_baseline.reference_op_config0).  8 distinct weight/output
+    pairs per pass (> L2), device time per launch."""
+    out = {"unit": "GB/s (block bytes + fp32 output bytes)", "cases": []}
+    launches = 0
+    for tname, t in (("Q4_0", 2), ("Q8_0", 8)):
+        ws = [torch.from_numpy(synth.random_blocks(t, 4096, 4096, seed=i)).to(dev) for i in range(8)]
+        outs = [torch.empty((4096, 4096), dtype=torch.float32, device=dev) for _ in range(8)]
+        for w, o in zip(ws, outs):
+            ggml.dequantize_out(w, t, 4096, 4096, o)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        a.record()
+        for _ in range(reps):
+            for w, o in zip(ws, outs):
+                ggml.dequantize_out(w, t, 4096, 4096, o)
+        b.record()
+        b.synchronize()
+        ms = a.elapsed_time(b) / (reps * 8)
+        launches += 8 * (reps + 1)
+        nbytes = ws[0].numel() + 4096 * 4096 * 4
+        out["cases"].append({"type": tname, "us_per_launch": ms * 1e3, "GBps": nbytes / (ms * 1e-3) / 1e9,
+                             "frac_of_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / float(peaks["hbm_gbs"])})
+    return out, launches
+
+
 def run(ggml, synth, dev, rank, world, peaks, peak_kind):
     extras = {}
     n = 0
@@ -191,7 +219,7 @@ def run(ggml, synth, dev, rank, world, peaks, peak_kind):
         if rank == 0:
             extras["tp_mlp"] = {"error": f"{type(e).__name__}: {e}"}
     if rank == 0:
-        for name, fn in (("mmvq", mmvq_section), ("mmq", mmq_section)):
+        for name, fn in (("config0_gpu", config0_section), ("mmvq", mmvq_section), ("mmq", mmq_section)):
             try:
                 extras[name], k = fn(ggml, synth, dev, peaks, peak_kind)
                 n += k

@@ -60,6 +60,9 @@ struct Params {
     int img_plane;           // token atoms (8 tokens) per K-plane of the B image (the full activation matrix's)
     int ntiles_run;          // cluster-level tiles this launch processes (the rest belongs to a tail launch)
     int off_b, off_raw, off_tab, off_epi, off_bar;
+    int pdl;                 // 0: the launch has no programmatic dependency to wait for (tail launch: its inputs were
+                             //    complete before the main launch released it); 1: wait before B loads and Y stores;
+                             //    2: as 1, and weights are static (raw weight tiles may be fetched before the wait)
     int y_vec;               // Y rows can take 16-byte stores (Y 16-byte aligned, ldy * sizeof(T) % 16 == 0)
 };
 
@@ -127,6 +130,8 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *t
 template <typename T, bool D_HALF>
 __global__ void __launch_bounds__(256)
 quantize_b_image_kernel(const T *__restrict__ x, uint8_t *__restrict__ img, int64_t M, int K, int Kp, int Mp, bool vec_ok) {
+    ggb_pdl_launch_dependents();        // the GEMM's CTAs may become resident (barriers, TMEM, raw weight tiles) meanwhile
+    ggb_pdl_wait();                     // x comes from, and the image may still be read by, the previous kernels
     const int groups_per_row = Kp / 32;
     const int64_t gid = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 2;
     const int t = threadIdx.x & 3;
@@ -215,6 +220,12 @@ mmq_kernel(const Params p, const __grid_constant__ CUtensorMap tmapW) {
 
     if (warp == 0) {
         // ============================ producer ============================
+        // Programmatic dependent launch: this CTA may be resident while the activation-image kernel still runs.
+        // Dependents are released only AFTER this kernel's own dependency has resolved, so a dependent that needs
+        // nothing newer than this kernel's inputs (the tail launch) may skip its wait and fill the SMs that the last
+        // round of this launch leaves idle.
+        bool waited = (p.pdl == 0);
+        if (p.pdl == 1) { ggb_pdl_wait(); waited = true; if (lane == 0) ggb_pdl_launch_dependents(); }
         int it = 0, rit = 0;
         for (int tile = cid; tile < ntiles; tile += ncl) {
             const int rb = (tile % n_rbg) * CL + crank, tg = tile / n_rbg;
@@ -243,6 +254,7 @@ mmq_kernel(const Params p, const __grid_constant__ CUtensorMap tmapW) {
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&raw_full[rs]);
                 }
+                if (!waited) { ggb_pdl_wait(); waited = true; if (lane == 0) ggb_pdl_launch_dependents(); }
                 for (int q = 0; q < RAWK / KSTEP; q++, it++) {
                     const int s = it % NSTAGE;
                     mbar_wait(&ab_empty[s], ((uint32_t)(it / NSTAGE) & 1u) ^ 1u);
@@ -262,6 +274,8 @@ mmq_kernel(const Params p, const __grid_constant__ CUtensorMap tmapW) {
                 }
             }
         }
+        if (!waited) { ggb_pdl_wait(); if (lane == 0) ggb_pdl_launch_dependents(); }
+        else if (p.pdl == 0 && lane == 0) ggb_pdl_launch_dependents();
     } else if (warp == 1) {
         // ============================ MMA issuer (one thread) ============================
         if (lane == 0) {
@@ -299,6 +313,7 @@ mmq_kernel(const Params p, const __grid_constant__ CUtensorMap tmapW) {
         // ============================ epilogue (4 warps = 4 TMEM lane quadrants) ============================
         const int quad = warp & 3;
         T *Y = static_cast<T *>(p.Y);
+        if (p.pdl) ggb_pdl_wait();                             // Y may still be read by the kernel before the image kernel
         int tcount = 0;
         for (int tile = cid; tile < ntiles; tile += ncl, tcount++) {
             const int rb = (tile % n_rbg) * CL + crank, tg = tile / n_rbg;
@@ -384,7 +399,11 @@ mmq_kernel(const Params p, const __grid_constant__ CUtensorMap tmapW) {
                         // warp = 8 consecutive rows of the same half: its 128-bit loads (row stride 144 B) and its swizzled
                         // 128-bit stores (chunk ^ (row & 7)) both touch 8 distinct 16-byte bank groups.
                         const int r = (u & 7) | ((u >> 4) << 3), half = (u >> 3) & 1;
-                        const uint2 sc = *reinterpret_cast<const uint2 *>(tab + r * HU::NSUB + 2 * q);
+                        // the two table words this thread's 32 values use: Q4_K sub-blocks 2q, 2q+1; Q6_K (16 per row, one per
+                        // 16 values) sub-blocks 4q + half and 4q + 2 + half
+                        uint2 sc;
+                        if constexpr (HU::NSUB == 8) sc = *reinterpret_cast<const uint2 *>(tab + r * HU::NSUB + 2 * q);
+                        else sc = make_uint2(tab[r * HU::NSUB + 4 * q + half], tab[r * HU::NSUB + 4 * q + 2 + half]);
                         uint4 o[4];
                         HU::run32(raw + r * p.raw_slot + slot_off, q, half, sc, o);
                         uint8_t *row = a_stage + r * 128;
@@ -425,6 +444,9 @@ mmq_kernel(const Params p, const __grid_constant__ CUtensorMap tmapW) {
         }
     }
 
+    // A tail launch did not wait for the main launch it overlaps with; the kernel AFTER it only waits for the tail, so the
+    // tail must not complete first: its CTAs wait for the main launch here, at their end.
+    if (p.pdl == 0) ggb_pdl_wait();
     tc_fence_before();
     if (CL == 1) __syncthreads();
     else cluster_sync_all();                                   // no CTA leaves while a peer may still signal or copy into it
@@ -457,9 +479,17 @@ int launch_quantize(const void *X, int64_t M, int64_t K, uint8_t *img, bool d_ha
         return GGB_E_SHAPE;
     }
     const T *x = static_cast<const T *>(X);
-    if (d_half) quantize_b_image_kernel<T, true><<<(unsigned)nblk, 256, 0, stream>>>(x, img, M, (int)K, (int)Kp, (int)Mp, vec_ok);
-    else        quantize_b_image_kernel<T, false><<<(unsigned)nblk, 256, 0, stream>>>(x, img, M, (int)K, (int)Kp, (int)Mp, vec_ok);
-    GGB_CUDA_TRY(cudaGetLastError());
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)nblk);
+    cfg.blockDim = dim3(256);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (d_half) GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, quantize_b_image_kernel<T, true>, x, img, M, (int)K, (int)Kp, (int)Mp, vec_ok));
+    else        GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, quantize_b_image_kernel<T, false>, x, img, M, (int)K, (int)Kp, (int)Mp, vec_ok));
     return GGB_OK;
 }
 
@@ -483,7 +513,7 @@ EncodeTiledFn get_encode_fn() {
 // run (-1: all)
 template <int TYPE, int BN, int NB, int CL, typename T>
 int launch_gemm(const void *W, const uint8_t *img, void *Y, int64_t M, int64_t K, int64_t N, int64_t ldy, cudaStream_t stream,
-                int img_plane = 0, int tile_limit = -1) {
+                int img_plane = 0, int tile_limit = -1, bool is_tail = false) {
     constexpr int NSTAGE = nstage_of(NB);
     constexpr int QK = BlockTraits<TYPE>::QK, BS = BlockTraits<TYPE>::BS;
     constexpr int SB_BYTES = RAWK / QK * BS;
@@ -501,6 +531,7 @@ int launch_gemm(const void *W, const uint8_t *img, void *Y, int64_t M, int64_t K
     p.Mp = (int)((M + BN - 1) / BN * BN);
     p.img_plane = img_plane > 0 ? img_plane : (int)(padded_m(M) >> 3);
     p.ntiles_run = tile_limit >= 0 ? tile_limit : 0x7fffffff;
+    p.pdl = is_tail ? 0 : (ggb_static_weights() ? 2 : 1);
     p.n_row_blocks = (int)((N + BM - 1) / BM);
     p.n_tok_tiles = p.Mp / BN;
     p.n_tok_groups = (p.n_tok_tiles + NB - 1) / NB;
@@ -557,13 +588,15 @@ int launch_gemm(const void *W, const uint8_t *img, void *Y, int64_t M, int64_t K
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmq_kernel<TYPE, BN, NB, CL, T>, p, tmap));
     return GGB_OK;
 }
@@ -598,7 +631,7 @@ int run_typed(const void *W, const void *X, void *Y, int64_t M, int64_t K, int64
                         const int64_t row_bytes = K / BlockTraits<TYPE>::QK * BlockTraits<TYPE>::BS;
                         return launch_gemm<TYPE, 64, 1, 1, T>(static_cast<const uint8_t *>(W) + row0 * row_bytes, img + (tok0 >> 3) * 1024,
                                                               static_cast<T *>(Y) + tok0 * ldy + row0, M - tok0, K, N - row0, ldy, stream,
-                                                              (int)(padded_m(M) >> 3));
+                                                              (int)(padded_m(M) >> 3), -1, /*is_tail=*/true);
                     }
                 }
             }

@@ -102,13 +102,57 @@ template <> struct HalfUnpack<T_Q5_K> {
     }
 };
 
+// 16 bytes from a 2-byte-aligned shared-memory address as four words (the misalignment is warp-uniform in the MMQ tile)
+__device__ __forceinline__ uint4 ld_u128_a2(const uint8_t *p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+    if (a & 2) {
+        const uint32_t w0 = q[0], w1 = q[1], w2 = q[2], w3 = q[3], w4 = q[4];
+        return make_uint4(__funnelshift_r(w0, w1, 16), __funnelshift_r(w1, w2, 16), __funnelshift_r(w2, w3, 16),
+                          __funnelshift_r(w3, w4, 16));
+    }
+    return make_uint4(q[0], q[1], q[2], q[3]);
+}
+
 template <> struct HalfUnpack<T_Q6_K> {
-    static constexpr bool HAS = true, FAST32 = false;
+    static constexpr bool HAS = true, FAST32 = true;
     static constexpr int NSUB = 16;
     __device__ __forceinline__ static int sub_of(int p) { return p >> 1; }
     __device__ __forceinline__ static uint32_t sub_scale(const uint8_t *b, int is) {     // {fp16(dl), 0}
         const float2 s = Unpack8<T_Q6_K>::sub_scale(b, is);
         return h2_as_u32(__floats2half2_rn(s.x, 0.0f));
+    }
+    // k-step q (64 columns) of a row = the 32-value groups r = 2 (q & 1), 2 (q & 1) + 1 of half ip = q >> 1; this thread
+    // takes l = 16 half .. 16 half + 15 of both: ql[64 ip + l] / ql[64 ip + 32 + l] (low nibbles for q even, high for q odd)
+    // and qh[32 ip + l] bits 2r..2r+1.  sc = the row's scale-table words {2q, 2q+1 | 2q+2, 2q+3}: entry 4 (q & 1) ... the
+    // caller passes the two table words of sub-blocks 8 ip + 2 r + half (first group) and 8 ip + 2 r + 2 + half (second).
+    __device__ __forceinline__ static void run32(const uint8_t *b, int q, int half, uint2 sc, uint4 (&o)[4]) {
+        const int ip = q >> 1, hi = q & 1;
+        const uint4 la = ld_u128_a2(b + 64 * ip + 16 * half), lb = ld_u128_a2(b + 64 * ip + 32 + 16 * half);
+        const uint4 qh = ld_u128_a2(b + 128 + 32 * ip + 16 * half);
+        const __half2 dl0 = u32_as_h2(__byte_perm(sc.x, sc.x, 0x1010)), dl1 = u32_as_h2(__byte_perm(sc.y, sc.y, 0x1010));
+        const __half2 k1056 = u32_as_h2(0x64206420u);                 // 1024 + 32: raw - 32 is the signed quant
+        const uint32_t a[4] = {la.x, la.y, la.z, la.w}, c[4] = {lb.x, lb.y, lb.z, lb.w}, h[4] = {qh.x, qh.y, qh.z, qh.w};
+        uint32_t lo[8], up[8];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            uint32_t t0, t1;
+            if (hi == 0) {
+                t0 = (a[i] & 0x0f0f0f0fu) | ((h[i] << 4) & 0x30303030u);
+                t1 = (c[i] & 0x0f0f0f0fu) | ((h[i] << 2) & 0x30303030u);
+            } else {
+                t0 = ((a[i] >> 4) & 0x0f0f0f0fu) | (h[i] & 0x30303030u);
+                t1 = ((c[i] >> 4) & 0x0f0f0f0fu) | ((h[i] >> 2) & 0x30303030u);
+            }
+            lo[2 * i] = h2_as_u32(__hmul2(__hsub2(magic_h2_lo(t0), k1056), dl0));
+            lo[2 * i + 1] = h2_as_u32(__hmul2(__hsub2(magic_h2_hi(t0), k1056), dl0));
+            up[2 * i] = h2_as_u32(__hmul2(__hsub2(magic_h2_lo(t1), k1056), dl1));
+            up[2 * i + 1] = h2_as_u32(__hmul2(__hsub2(magic_h2_hi(t1), k1056), dl1));
+        }
+        o[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        o[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+        o[2] = make_uint4(up[0], up[1], up[2], up[3]);
+        o[3] = make_uint4(up[4], up[5], up[6], up[7]);
     }
     __device__ __forceinline__ static uint4 run(const uint8_t *b, int p, uint32_t sc) {
         const int ip = p >> 4, r = (p >> 2) & 3, l0 = (p & 3) * 8;

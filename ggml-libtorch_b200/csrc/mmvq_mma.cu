@@ -72,7 +72,9 @@ struct MmaParams {
     int slot_row_stride;   // bytes between rows of a slot = chunk bytes (the TMA box is dense)
     int slot_stride;
     int depth;             // ring slots per warp
-    int off_scr, off_part, off_slots, off_bars;
+    int accy_rgs;          // row groups per team in the phase accumulator (P > 1)
+    int phases;            // K phases: the shared-memory image holds K / phases columns at a time (1: the whole row)
+    int off_scr, off_part, off_accy, off_slots, off_bars;
     int row_bytes;
     unsigned long long *trace;   // debug: per-CTA globaltimer stamps {start, dependency resolved, activations in, end}
     int pdl_prefetch;
@@ -362,13 +364,17 @@ template <> struct MmaOps<T_Q6_K> {
 // ------------------------------------------------------------------------------------------------
 // launch 2: the GEMV
 // ------------------------------------------------------------------------------------------------
-template <int TYPE, typename T, int NW>
+// PHASED = false: the whole activation image is resident (P == 1 at compile time: the common case keeps its code)
+template <int TYPE, typename T, int NW, bool PHASED>
 __global__ void __launch_bounds__(NW * 32, 1)
 mmvq_mma_kernel(const MmaParams p, const __grid_constant__ CUtensorMap tmapW) {
     using Ops = MmaOps<TYPE>;
     extern __shared__ __align__(128) uint8_t smem[];
-    const ActLayout L = act_layout(p.B, p.K, Ops::S16);
+    const int P = PHASED ? p.phases : 1, pc = PHASED ? p.nchunks / P : p.nchunks;   // chunks per phase (P divides nchunks)
+    const ActLayout Lg = act_layout(p.B, p.K, Ops::S16);                        // the image in the workspace
+    const ActLayout L = act_layout(p.B, p.K / P, Ops::S16);                     // one phase of it in shared memory
     int *scr_all = reinterpret_cast<int *>(smem + p.off_scr);                   // [NW][2][kScrWords]
+    float4 *accy = reinterpret_cast<float4 *>(smem + p.off_accy);               // [team][row group][32] (P > 1)
     float4 *part = reinterpret_cast<float4 *>(smem + p.off_part);               // [2][NW][32]
     uint8_t *slots = smem + p.off_slots;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + p.off_bars);
@@ -398,23 +404,27 @@ mmvq_mma_kernel(const MmaParams p, const __grid_constant__ CUtensorMap tmapW) {
     const int S = 1 << p.s_log2, NT = NW >> p.s_log2;
     const int team = warp >> p.s_log2, s = warp & (S - 1);
     const int my_rgs = (nrg - team + NT - 1) / NT;                 // may be <= 0
-    const int my_chunks = (p.nchunks - s + S - 1) >> p.s_log2;      // >= 1 (S <= nchunks)
-    const int my_units = my_rgs > 0 ? my_rgs * my_chunks : 0;
+    const int my_chunks = (pc - s + S - 1) >> p.s_log2;             // per phase; >= 1 (S <= pc)
+    const int my_units = my_rgs > 0 ? my_rgs * my_chunks * P : 0;
     const int ring_base = warp * p.depth;
     const uint64_t pol = l2_policy_evict_first();
 
-    // issue state, warp-uniform: the next unit (row group, chunk) of this warp to stream
-    int is_k = 0, is_ring = ring_base, is_rg = team, is_c = s;
+    // issue state, warp-uniform: the next unit (phase, row group, chunk) of this warp to stream
+    int is_k = 0, is_ring = ring_base, is_rg = team, is_c = s, is_ph = 0;
     auto issue_next = [&]() {                                      // whole warp (lane 0 issues)
         if (lane == 0) {
             // rows past N and bytes past the row end are zero-filled by the TMA unit and count as transferred
             // (blocks that are not multiples of 16 bytes: the box starts at the 16-byte boundary below the chunk)
             mbar_expect_tx(&full[is_ring], (uint32_t)(kRowsPerGroup * p.slot_row_stride));
-            tma_load_2d_hint(slots + is_ring * p.slot_stride, &tmapW, ((is_c * p.cs * Ops::BS) & ~15) >> 2,
+            tma_load_2d_hint(slots + is_ring * p.slot_stride, &tmapW, (((is_ph * pc + is_c) * p.cs * Ops::BS) & ~15) >> 2,
                              (int)r_begin + is_rg * kRowsPerGroup, &full[is_ring], pol);
         }
         is_c += S;
-        if (is_c >= p.nchunks) { is_c = s; is_rg += NT; }
+        if (is_c >= pc) {
+            is_c = s;
+            is_rg += NT;
+            if (is_rg >= nrg) { is_rg = team; is_ph++; }
+        }
         is_k++;
         if (++is_ring == ring_base + p.depth) is_ring = ring_base;
     };
@@ -423,12 +433,29 @@ mmvq_mma_kernel(const MmaParams p, const __grid_constant__ CUtensorMap tmapW) {
         while (is_k < min(p.depth, my_units)) issue_next();
     pdl_wait();                                                    // the activation image is complete
     if (p.trace && tid == 0) p.trace[blockIdx.x * 4 + 1] = gtime();
-    if (warp == NW - 1 && lane == 0) {                             // (the last warp has the fewest units to prime)
-        mbar_expect_tx(act_full, (uint32_t)L.total);
-        constexpr int kPiece = 32768;
-        for (int off = 0; off < L.total; off += kPiece)
-            bulk_g2s(smem + off, p.act_img + off, (uint32_t)min(kPiece, L.total - off), act_full);
-    }
+    // phase `ph` of the activation image: the whole image in one piece when P == 1, else the K-slice of every token's
+    // quants and of both scale tables
+    auto load_image = [&](int ph) {                                // one thread
+        if (P == 1) {
+            mbar_expect_tx(act_full, (uint32_t)L.total);
+            constexpr int kPiece = 32768;
+            for (int off = 0; off < L.total; off += kPiece)
+                bulk_g2s(smem + off, p.act_img + off, (uint32_t)min(kPiece, L.total - off), act_full);
+            return;
+        }
+        const int Kp = p.K / P, k0 = ph * Kp, g0 = k0 >> 5, ngp = Kp >> 5, npairs = (p.B + 1) >> 1;
+        const int sm = Ops::S16 ? 2 : 1;
+        mbar_expect_tx(act_full, (uint32_t)(p.B * Kp + npairs * ngp * 8 + p.B * ngp * sm * 8));
+        for (int b = 0; b < p.B; b++)
+            bulk_g2s(smem + b * L.act_stride, p.act_img + b * Lg.act_stride + k0, (uint32_t)Kp, act_full);
+        for (int pr = 0; pr < npairs; pr++)
+            bulk_g2s(smem + L.off_d + pr * L.d_stride2 * 8, p.act_img + Lg.off_d + (pr * Lg.d_stride2 + g0) * 8,
+                     (uint32_t)(ngp * 8), act_full);
+        for (int b = 0; b < p.B; b++)
+            bulk_g2s(smem + L.off_s + b * L.s_stride2 * 8, p.act_img + Lg.off_s + (b * Lg.s_stride2 + g0 * sm) * 8,
+                     (uint32_t)(ngp * sm * 8), act_full);
+    };
+    if (warp == NW - 1 && lane == 0) load_image(0);                // (the last warp has the fewest units to prime)
     if (!p.pdl_prefetch)
         while (is_k < min(p.depth, my_units)) issue_next();
     mbar_wait(act_full, 0);
@@ -444,18 +471,29 @@ mmvq_mma_kernel(const MmaParams p, const __grid_constant__ CUtensorMap tmapW) {
     int ring = ring_base;
     uint32_t phase = 0;
     int step_no = 0;
+    for (int ph = 0; ph < P; ph++) {
+    if (ph > 0) {
+        // every warp is done with the previous K-slice of the image: fetch the next one over it
+        __syncthreads();
+        if (warp == NW - 1 && lane == 0) {
+            fence_proxy_async();
+            load_image(ph);
+        }
+        mbar_wait(act_full, ph & 1);
+    }
     for (int rgi = 0; rgi < my_rgs; rgi++) {
         const int rg = team + rgi * NT;
         float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-        for (int c = s; c < p.nchunks; c += S) {
-            const int sb0 = c * p.cs;
+        for (int cl = s; cl < pc; cl += S) {
+            const int sbl0 = cl * p.cs;                            // first super-block of the chunk inside this phase
+            const int sb0 = ph * pc * p.cs + sbl0;                 // ... and inside the row
             const int nsbc = min(p.cs, nsb - sb0);
             mbar_wait(&full[ring], phase);
             const uint8_t *r0 = slots + ring * p.slot_stride + q * p.slot_row_stride + ((sb0 * Ops::BS) & 15);
             const uint8_t *r1 = r0 + 8 * p.slot_row_stride;
 #pragma unroll 1
             for (int i = 0; i < nsbc; i++) {
-                const int sb = sb0 + i;
+                const int sb = sbl0 + i;
                 Ops::step(r0 + i * Ops::BS, r1 + i * Ops::BS, act_tok + sb * 256, d_pair + sb * 8, s_tok + sb * (Ops::S16 ? 16 : 8),
                           scr + (step_no & 1) * kScrWords, q, t, acc);
                 step_no++;
@@ -469,7 +507,7 @@ mmvq_mma_kernel(const MmaParams p, const __grid_constant__ CUtensorMap tmapW) {
         }
         // partial sums of the team's warps meet in shared memory and are added in warp order
         if (S > 1) {
-            float4 *pb = part + (rgi & 1) * (NW * 32);
+            float4 *pb = part + ((ph * my_rgs + rgi) & 1) * (NW * 32);
             pb[warp * 32 + lane] = make_float4(acc[0], acc[1], acc[2], acc[3]);
             named_bar_sync(1 + team, S * 32);
             if (s == 0) {
@@ -482,7 +520,16 @@ mmvq_mma_kernel(const MmaParams p, const __grid_constant__ CUtensorMap tmapW) {
                 acc[0] = v.x; acc[1] = v.y; acc[2] = v.z; acc[3] = v.w;
             }
         }
-        if (s == 0) {
+        if (s == 0 && P > 1) {
+            // the row group's sum over the phases so far lives in shared memory (only this warp touches its entry)
+            float4 *a = accy + (team * p.accy_rgs + rgi) * 32 + lane;
+            if (ph > 0) {
+                const float4 o = *a;
+                acc[0] += o.x; acc[1] += o.y; acc[2] += o.z; acc[3] += o.w;
+            }
+            if (ph + 1 < P) *a = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        }
+        if (s == 0 && ph + 1 == P) {
             const int lr = rg * kRowsPerGroup + q;
             const int tok = 2 * t;
             if (lr < nrows) {
@@ -494,6 +541,7 @@ mmvq_mma_kernel(const MmaParams p, const __grid_constant__ CUtensorMap tmapW) {
                 if (tok + 1 < p.B) ggb_yout_store<T>(p.yo, tok + 1, r_begin + lr + 8, acc[3]);
             }
         }
+    }
     }
     if (p.trace && tid == 0) p.trace[blockIdx.x * 4 + 3] = gtime();
 }
@@ -513,25 +561,34 @@ namespace {
 
 // fills p and the shared-memory size for NW warps and `cs` super-blocks per chunk; false if the ring would be too shallow
 template <int TYPE>
-bool plan(MmaParams &p, int &smem, int NW, int cs, int B, int K, int max_smem) {
+bool plan(MmaParams &p, int &smem, int NW, int cs, int P, int B, int K, int64_t N, int grid, int max_smem) {
     using Ops = MmaOps<TYPE>;
-    const ActLayout L = act_layout(B, K, Ops::S16);
     p.cs = cs < p.nsb ? cs : p.nsb;
     // TMA box: the chunk's bytes, from the 16-byte boundary at or below its start (Q6_K: 210-byte blocks)
     const int rs = (Ops::BS % 16 == 0) ? p.cs * Ops::BS : ((p.cs * Ops::BS + 14 + 15) & ~15);
     if (rs > 1024) return false;                               // TMA box <= 256 uint32 elements
     p.nchunks = (p.nsb + p.cs - 1) / p.cs;
+    if (P > 1 && (p.nsb % p.cs != 0 || p.nchunks % P != 0 || (K / P) % 512 != 0)) return false;
+    p.phases = P;
+    const ActLayout L = act_layout(B, K / P, Ops::S16);
+    const int pc = p.nchunks / P;
     int sl = 0;
-    while ((2 << sl) <= p.nchunks && (2 << sl) <= NW) sl++;      // S = largest power of two <= min(nchunks, NW)
-    if (g_s_log2 >= 0 && (1 << g_s_log2) <= p.nchunks && (1 << g_s_log2) <= NW) sl = g_s_log2;
+    while ((2 << sl) <= pc && (2 << sl) <= NW) sl++;             // S = largest power of two <= min(chunks per phase, NW)
+    if (g_s_log2 >= 0 && (1 << g_s_log2) <= pc && (1 << g_s_log2) <= NW) sl = g_s_log2;
     p.s_log2 = sl;
     p.slot_row_stride = rs;
     p.slot_stride = (kRowsPerGroup * rs + 127) & ~127;
     p.off_scr = (L.total + 127) & ~127;
     p.off_part = p.off_scr + NW * 2 * kScrWords * 4;
-    p.off_slots = (p.off_part + 2 * NW * 32 * 16 + 127) & ~127;
+    p.off_accy = p.off_part + 2 * NW * 32 * 16;
+    const int NT = NW >> sl;
+    const int64_t ngr = (N + kRowsPerGroup - 1) / kRowsPerGroup;
+    const int nrg_max = (int)((ngr + grid - 1) / grid) + 1;
+    p.accy_rgs = (nrg_max + NT - 1) / NT;
+    p.off_slots = (p.off_accy + (P > 1 ? NT * p.accy_rgs * 32 * 16 : 0) + 127) & ~127;
     const int bar_bytes = (kMaxSlots + 1) * 8;
     const int avail = max_smem - p.off_slots - bar_bytes - 128;
+    if (avail <= 0) return false;
     int depth = avail / (p.slot_stride * NW);
     if (depth < 2) return false;
     if (depth > kMaxSlots / NW) depth = kMaxSlots / NW;
@@ -542,12 +599,12 @@ bool plan(MmaParams &p, int &smem, int NW, int cs, int B, int K, int max_smem) {
     return true;
 }
 
-template <int TYPE, typename T, int NW>
+template <int TYPE, typename T, int NW, bool PHASED>
 int launch_gemv(MmaParams &p, int smem, const CUtensorMap &tmap, cudaStream_t stream) {
     const DeviceInfo &di = ggb_device_info();
     static bool attr_set[64] = {};
     if (!attr_set[di.dev]) {
-        GGB_CUDA_TRY(cudaFuncSetAttribute(mmvq_mma_kernel<TYPE, T, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        GGB_CUDA_TRY(cudaFuncSetAttribute(mmvq_mma_kernel<TYPE, T, NW, PHASED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           di.max_smem_optin));
         attr_set[di.dev] = true;
     }
@@ -564,7 +621,7 @@ int launch_gemv(MmaParams &p, int smem, const CUtensorMap &tmap, cudaStream_t st
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmvq_mma_kernel<TYPE, T, NW>, p, tmap));
+    GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmvq_mma_kernel<TYPE, T, NW, PHASED>, p, tmap));
     return GGB_OK;
 }
 
@@ -582,12 +639,19 @@ int launch(const void *W, const void *X, void *Y, int64_t B, int64_t K, int64_t 
     p.row_bytes = p.nsb * Ops::BS;
     p.pdl_prefetch = ggb_mmvq_static_weights();
     if (p.row_bytes % 16 != 0 || N > 0x7fffffff) return 1;
-    // preferred chunk: 2 super-blocks for short rows (more K-parallelism), 4 for long ones; smaller if the ring needs it
+    // preferred chunk: 2 super-blocks for short rows (more K-parallelism), 4 for long ones; smaller if the ring needs it.
+    // If the whole activation image does not fit beside a useful ring (long rows x large batch), the row is walked in
+    // K phases with one slice of the image resident at a time.
     const int pref = g_cs > 0 ? g_cs : (p.nsb <= 16 ? 2 : 4);
+    const int64_t ngr_all = (N + kRowsPerGroup - 1) / kRowsPerGroup;
+    const int grid_est = (int)(ngr_all < di.sm_count ? ngr_all : di.sm_count);
     int smem = 0, nw = 0;
-    for (int NW : {16, 8}) {
-        for (int cs = pref; cs >= 1 && !nw; cs >>= 1)
-            if (plan<TYPE>(p, smem, NW, cs, (int)B, (int)K, di.max_smem_optin)) nw = NW;
+    for (int P : {1, 2, 4, 7, 8, 14, 16}) {
+        for (int NW : {16, 8}) {
+            for (int cs = pref; cs >= 1 && !nw; cs >>= 1)
+                if (plan<TYPE>(p, smem, NW, cs, P, (int)B, (int)K, N, grid_est, di.max_smem_optin)) nw = NW;
+            if (nw) break;
+        }
         if (nw) break;
     }
     if (!nw) return 1;
@@ -614,7 +678,9 @@ int launch(const void *W, const void *X, void *Y, int64_t B, int64_t K, int64_t 
         GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmvq_act_image_kernel<T, Ops::S16>, static_cast<const T *>(X), static_cast<uint8_t *>(ws),
                                         (int)B, (int)K, x_vec));
     }
-    return nw == 16 ? launch_gemv<TYPE, T, 16>(p, smem, tmap, stream) : launch_gemv<TYPE, T, 8>(p, smem, tmap, stream);
+    if (p.phases == 1)
+        return nw == 16 ? launch_gemv<TYPE, T, 16, false>(p, smem, tmap, stream) : launch_gemv<TYPE, T, 8, false>(p, smem, tmap, stream);
+    return nw == 16 ? launch_gemv<TYPE, T, 16, true>(p, smem, tmap, stream) : launch_gemv<TYPE, T, 8, true>(p, smem, tmap, stream);
 }
 
 template <int TYPE>

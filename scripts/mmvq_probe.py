@@ -30,7 +30,7 @@ if "shapes" in opt:
 if "check" in args or not [a for a in args if "=" not in a]:
     for t in types:
         for (N, K, B) in [(1, 256, 1), (5, 512, 3), (96, 1024, 2), (300, 4096, 1), (64, 6144, 3), (33, 2304, 2), (257, 2048, 8),
-                          (257, 2048, 5), (1000, 14336, 1), (999, 8192, 4), (14336, 4096, 1), (14336, 4096, 8), (4096, 14336, 3), (1001, 2304, 7)]:
+                          (257, 2048, 5), (1000, 14336, 1), (999, 8192, 4), (14336, 4096, 1), (14336, 4096, 8), (4096, 14336, 3), (1001, 2304, 7), (515, 28672, 8), (130, 14336, 8), (77, 16384, 6)]:
             w = oracle.random_weights(t, N, K, seed=1)
             x = torch.randn(B, K, generator=torch.Generator().manual_seed(0))
             want = oracle.mmvq(w, t, x.numpy(), N)
