@@ -5,7 +5,7 @@
 """
 import os, sys, statistics
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path[:0] = [ROOT, os.path.join(ROOT, "ggml-libtorch_b200"), os.path.join(ROOT, "tests")]
+sys.path[:0] = [ROOT, os.environ.get("GGML_PKG_DIR", os.path.join(ROOT, "ggml-libtorch_b200")), os.path.join(ROOT, "tests")]
 import numpy as np, torch
 import oracle, ggml
 from ggml import synth, _capi

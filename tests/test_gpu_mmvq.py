@@ -90,6 +90,38 @@ def test_config3_llama8b_shapes(ops, t, shape):
         _check(ops, t, N, K, B, torch.float16, seed=B)
 
 
+@pytest.mark.parametrize("case", [(oracle.Q4_K, 130, 28672, 8), (oracle.Q6_K, 70, 14336, 8), (oracle.Q6_K, 40, 28672, 6),
+                                  (oracle.Q5_K, 50, 28672, 7), (oracle.Q4_K, 33, 14336, 2)],
+                         ids=["Q4_K-K28672-B8", "Q6_K-K14336-B8", "Q6_K-K28672-B6", "Q5_K-K28672-B7", "Q4_K-K14336-B2"])
+def test_long_rows_k_phases(ops, case):
+    """long rows x large batches: the q8_1 activation image does not fit in shared memory next to the weight ring, so
+    the tensor-core kernel walks the row in K phases (and batch 2 takes that kernel only for K > 8192)."""
+    t, N, K, B = case
+    _check(ops, t, N, K, B, torch.float16, seed=B)
+    _check(ops, t, N, K, B, torch.float32, seed=B + 1)
+
+
+@pytest.mark.parametrize("case", [(oracle.Q4_K, 1), (oracle.Q4_K, 2), (oracle.Q4_K, 5), (oracle.Q6_K, 8), (oracle.Q5_K, 3)],
+                         ids=["Q4_K-B1", "Q4_K-B2", "Q4_K-B5", "Q6_K-B8", "Q5_K-B3"])
+def test_gather_epilogue_single_gpu(ops, case):
+    """ggb_mmvq_gather with two 'peer' buffers on one GPU: every result lands at [tok, col_offset + row] of BOTH
+    buffers, bit-identical to the plain op; nothing outside the slice is touched."""
+    t, B = case
+    N, K, ld, col0 = 264, 2048, 1000, 304
+    w = torch.from_numpy(oracle.random_weights(t, N, K, seed=t)).cuda()
+    x = torch.randn(B, K, generator=torch.Generator().manual_seed(B)).to(torch.float16).cuda()
+    want = ops.ggml_mul_mat_vec_a8(w, x, t, N)
+    bufs = [torch.full((8, ld), 7.0, dtype=torch.float16, device="cuda") for _ in range(2)]
+    ops.mul_mat_vec_a8_gather(w, x, t, N, [b.data_ptr() for b in bufs], ld, col0)
+    torch.cuda.synchronize()
+    for b in bufs:
+        assert torch.equal(b[:B, col0:col0 + N], want)
+        assert bool((b[:B, :col0] == 7.0).all()) and bool((b[:B, col0 + N:] == 7.0).all()) and bool((b[B:] == 7.0).all())
+    with pytest.raises(ValueError):          # Q8_0 is not on the fused path
+        w8 = torch.from_numpy(oracle.random_weights(oracle.Q8_0, 8, 256, seed=0)).cuda()
+        ops.mul_mat_vec_a8_gather(w8, x[:, :256].contiguous(), oracle.Q8_0, 8, [bufs[0].data_ptr()], ld, 0)
+
+
 def test_linearity_property(ops):
     """size-independent property at full size: rows of Y are independent, so a row-slice of W gives the
     same values as the slice of the full result (bit-for-bit: same K order per row)."""
