@@ -124,10 +124,18 @@ def tp_mlp_section(ggml, synth, dev, rank, world, peaks, peak_kind):
         w = torch.from_numpy(synth.random_blocks(t, n_local, k, seed=seed + 1000 * rank)).to(dev)
         return ColumnParallelQuantLinear(w, t, n_total, rank, world, fused_gather=fused)
 
-    variants = [("nccl all-gather", False)] + ([("fused peer stores + barrier (ggb_mmvq_gather)", True)] if world > 1 else [])
+    from ggml.parallel import FusedQuantMLP
+    variants = [("nccl all-gather" if world > 1 else "none (tp=1)", False)]
+    if world > 1:
+        variants.append(("fused peer stores + barrier (ggb_mmvq_gather)", True))
     mlps = {}
     for name, fused in variants:
         mlps[name] = QuantMLP(shard(12, I, H, 1, fused), shard(12, I, H, 2, fused), shard(14, H, I, 3, fused))
+    # the whole block as two launches: stacked gate|up with split output columns, SwiGLU inside the down projection
+    block_name = "fused block: 2 launches (stacked gate|up, SwiGLU in the down projection)" + (" + 2 barriers" if world > 1 else "")
+    base = mlps[variants[0][0]]
+    mlps[block_name] = FusedQuantMLP(base.gate, base.up, base.down)
+    variants.append((block_name, True))
     mlp = mlps[variants[0][0]]
     layer_bytes = sum(l.W.numel() for l in (mlp.gate, mlp.up, mlp.down)) * world
     out = {"unit": "us per MLP block (device time, max over ranks)", "tp": world,
@@ -169,7 +177,7 @@ def tp_mlp_section(ggml, synth, dev, rank, world, peaks, peak_kind):
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
             ms = float(tm.item())
         launches += (iters + 3) * 3
-        case = {"M": M, "exchange": name if world > 1 else "none (tp=1)", "us": ms * 1e3, "timing": how}
+        case = {"M": M, "exchange": name, "us": ms * 1e3, "timing": how}
         if M <= 8:
             case["weight_GBps_aggregate"] = layer_bytes / (ms * 1e-3) / 1e9
             case["frac_of_hbm_peak_per_gpu"] = layer_bytes / world / (ms * 1e-3) / 1e9 / float(peaks["hbm_gbs"])

@@ -90,7 +90,9 @@ static bool check_dtype(const char *fn, int dt) {
 
 // ---------------------------------------------------------------- gather target (see GgbYOut, ggb_common.cuh)
 static thread_local const GgbYOut *g_yout = nullptr;
+static thread_local const GgbXIn *g_xin = nullptr;
 const GgbYOut *ggb_current_yout() { return g_yout; }
+const GgbXIn *ggb_current_xin() { return g_xin; }
 
 extern "C" {
 
@@ -200,28 +202,34 @@ static int check_matmul(const char *fn, const void *W, const void *X, const void
     return GGB_OK;
 }
 
-int ggb_mmvq_gather(const void *W, const void *X, int type, int xy_dtype, int64_t B, int64_t K, int64_t N,
-                    void *const *y_peers, int n_peers, int64_t ldy, int64_t col_offset, void *ws, int64_t ws_bytes,
-                    void *stream) {
+int ggb_mmvq_fused(const void *W, const void *X, const void *X2, int64_t ldx, int type, int xy_dtype, int64_t B, int64_t K,
+                   int64_t N, void *const *y_peers, int n_peers, int64_t ldy, int64_t col_offset, int64_t split_row,
+                   int64_t col_offset2, void *ws, int64_t ws_bytes, void *stream) {
     g_err[0] = 0;
-    if (!y_peers || n_peers < 1 || n_peers > 8 || ldy < col_offset + N || col_offset < 0) {
-        ggb_set_error("ggb_mmvq_gather: need 1..8 output buffers and col_offset + N <= ldy");
+    const bool split = split_row > 0 && split_row < N;
+    if (!y_peers || n_peers < 1 || n_peers > 8 || col_offset < 0 || ldx < K ||
+        (split ? (col_offset + split_row > ldy || col_offset2 < 0 || col_offset2 + (N - split_row) > ldy) : col_offset + N > ldy)) {
+        ggb_set_error("ggb_mmvq_fused: need 1..8 output buffers, ldx >= K and every output column inside ldy");
         return GGB_E_ARG;
     }
     for (int i = 0; i < n_peers; i++)
         if (!y_peers[i] || (reinterpret_cast<uintptr_t>(y_peers[i]) & 3)) {
-            ggb_set_error("ggb_mmvq_gather: output buffer %d is null or not 4-byte aligned", i);
+            ggb_set_error("ggb_mmvq_fused: output buffer %d is null or not 4-byte aligned", i);
             return GGB_E_ARG;
         }
-    const int rc0 = check_matmul("ggb_mmvq_gather", W, X, y_peers[0], type, xy_dtype, B, K, N);
+    if (X2 && (reinterpret_cast<uintptr_t>(X2) & 3)) {
+        ggb_set_error("ggb_mmvq_fused: X2 must be 4-byte aligned");
+        return GGB_E_ARG;
+    }
+    const int rc0 = check_matmul("ggb_mmvq_fused", W, X, y_peers[0], type, xy_dtype, B, K, N);
     if (rc0 < 0) return rc0;
     if (rc0 > 0) return GGB_OK;
     if (B > 8) {
-        ggb_set_error("ggb_mmvq_gather: batch %lld > 8", (long long)B);
+        ggb_set_error("ggb_mmvq_fused: batch %lld > 8", (long long)B);
         return GGB_E_SHAPE;
     }
     if (ggb_mmvq_workspace_bytes(type, B, K, N) > ws_bytes || (ws_bytes > 0 && !ws)) {
-        ggb_set_error("ggb_mmvq_gather: workspace too small (%lld < %lld)", (long long)ws_bytes,
+        ggb_set_error("ggb_mmvq_fused: workspace too small (%lld < %lld)", (long long)ws_bytes,
                       (long long)ggb_mmvq_workspace_bytes(type, B, K, N));
         return GGB_E_ARG;
     }
@@ -230,17 +238,31 @@ int ggb_mmvq_gather(const void *W, const void *X, int type, int xy_dtype, int64_
     y.n = n_peers;
     y.ld = ldy;
     y.col0 = col_offset;
+    y.split = split ? split_row : 0x7fffffffffffffffLL;
+    y.col1 = split ? col_offset2 : 0;
+    GgbXIn x = {};
+    x.x2 = X2;
+    x.ldx = ldx;
     g_yout = &y;
+    g_xin = &x;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int rc = ggb_mmvq_mma_impl(W, X, nullptr, type, xy_dtype, B, K, N, ws, ws_bytes, st);
     if (rc == 1) rc = ggb_mmvq_sb_impl(W, X, nullptr, type, xy_dtype, B, K, N, st);
     g_yout = nullptr;
+    g_xin = nullptr;
     if (rc == 1) {
-        ggb_set_error("ggb_mmvq_gather: type %d with B=%lld, K=%lld is not on the fused path (use ggb_mmvq + an all-gather)",
+        ggb_set_error("ggb_mmvq_fused: type %d with B=%lld, K=%lld is not on the fused path (use ggb_mmvq + an all-gather)",
                       type, (long long)B, (long long)K);
         return GGB_E_SHAPE;
     }
     return rc;
+}
+
+int ggb_mmvq_gather(const void *W, const void *X, int type, int xy_dtype, int64_t B, int64_t K, int64_t N,
+                    void *const *y_peers, int n_peers, int64_t ldy, int64_t col_offset, void *ws, int64_t ws_bytes,
+                    void *stream) {
+    return ggb_mmvq_fused(W, X, nullptr, K, type, xy_dtype, B, K, N, y_peers, n_peers, ldy, col_offset, 0, 0, ws, ws_bytes,
+                          stream);
 }
 
 int64_t ggb_mmvq_workspace_bytes(int type, int64_t B, int64_t K, int64_t N) {

@@ -122,9 +122,18 @@ struct GgbYOut {
     void *base[8];
     int n;
     long long ld, col0;
+    long long split, col1;     // rows >= split go to column col1 + (row - split): two stacked projections (gate | up)
 };
-// thread-local target installed by ggb_mmvq_gather for the duration of its call (nullptr: the plain Y argument)
+// Activation source of the MMVQ kernels: X [B, K] with row stride ldx; with x2 != nullptr the activation is
+// SwiGLU(X, X2) = silu(X) * X2 computed on the fly with torch's eager roundings (silu and the product each rounded to
+// the tensor dtype), so a fused down-projection equals  mmvq(W, F.silu(g) * u)  bit for bit.
+struct GgbXIn {
+    const void *x2;
+    long long ldx;
+};
+// thread-local targets installed by ggb_mmvq_fused for the duration of its call (nullptr: the plain arguments)
 const GgbYOut *ggb_current_yout();
+const GgbXIn *ggb_current_xin();
 inline GgbYOut ggb_make_yout(void *Y, long long N) {
     if (const GgbYOut *g = ggb_current_yout()) return *g;
     GgbYOut y = {};
@@ -132,20 +141,37 @@ inline GgbYOut ggb_make_yout(void *Y, long long N) {
     y.n = 1;
     y.ld = N;
     y.col0 = 0;
+    y.split = 0x7fffffffffffffffLL;
+    y.col1 = 0;
     return y;
+}
+inline GgbXIn ggb_make_xin(long long K) {
+    if (const GgbXIn *x = ggb_current_xin()) return *x;
+    GgbXIn x = {};
+    x.x2 = nullptr;
+    x.ldx = K;
+    return x;
 }
 #ifdef __CUDACC__
 template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <typename T>
 __device__ __forceinline__ void ggb_yout_store(const GgbYOut &y, long long tok, long long row, float v) {
     const T h = from_f32<T>(v);
-    const long long idx = tok * y.ld + y.col0 + row;
+    const long long idx = tok * y.ld + (row < y.split ? y.col0 + row : y.col1 + (row - y.split));
     static_cast<T *>(y.base[0])[idx] = h;
     // (the plain op must not pay for the gather: a predicated 8-way loop here cost the batch-2 dp4a kernel 19 %)
     if (y.n > 1) {
 #pragma unroll 1
         for (int i = 1; i < y.n; i++) static_cast<T *>(y.base[i])[idx] = h;
     }
+}
+// silu(g) * u as torch eager computes it for tensors of dtype T: x / (1 + exp(-x)) in fp32, rounded to T, times u in
+// fp32, rounded to T  (aten/native/cuda/ActivationSiluKernel.cu, BinaryMulKernel.cu; identity roundings for fp32)
+template <typename T>
+__device__ __forceinline__ float ggb_swiglu(float g, float u) {
+    const float s = to_f32<T>(from_f32<T>(g / (1.0f + expf(-g))));
+    return to_f32<T>(from_f32<T>(s * u));
 }
 #endif
 

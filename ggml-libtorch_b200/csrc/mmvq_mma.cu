@@ -121,7 +121,7 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1
 // ------------------------------------------------------------------------------------------------
 template <typename T, bool S16>
 __global__ void __launch_bounds__(256)
-mmvq_act_image_kernel(const T *__restrict__ X, uint8_t *__restrict__ img, int B, int K, int x_vec) {
+mmvq_act_image_kernel(const T *__restrict__ X, const GgbXIn xin, uint8_t *__restrict__ img, int B, int K, int x_vec) {
     pdl_launch_dependents();
     pdl_wait();                                             // X comes from the previous kernel of the stream
     const ActLayout L = act_layout(B, K, S16);
@@ -133,7 +133,7 @@ mmvq_act_image_kernel(const T *__restrict__ X, uint8_t *__restrict__ img, int B,
     const int b = gi / ng, g = gi - b * ng;
     float v[8];
     if (b < B) {
-        load8_f32<T>(X + (int64_t)b * K + g * 32 + t4 * 8, x_vec != 0, v);
+        load_act8<T>(X, static_cast<const T *>(xin.x2), xin.ldx, b, g * 32 + t4 * 8, x_vec != 0, v);
     } else {
 #pragma unroll
         for (int i = 0; i < 8; i++) v[i] = 0.0f;            // the missing token of an odd batch: zero scales
@@ -674,8 +674,10 @@ int launch(const void *W, const void *X, void *Y, int64_t B, int64_t K, int64_t 
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        const int x_vec = (reinterpret_cast<uintptr_t>(X) & 15) == 0;
-        GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmvq_act_image_kernel<T, Ops::S16>, static_cast<const T *>(X), static_cast<uint8_t *>(ws),
+        const GgbXIn xin = ggb_make_xin(K);
+        const int x_vec = (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(xin.x2) & 15) == 0 &&
+                          (xin.ldx * (int64_t)sizeof(T)) % 16 == 0;
+        GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmvq_act_image_kernel<T, Ops::S16>, static_cast<const T *>(X), xin, static_cast<uint8_t *>(ws),
                                         (int)B, (int)K, x_vec));
     }
     if (p.phases == 1)
@@ -726,7 +728,7 @@ int ggb_mmvq_mma_impl(const void *W, const void *X, void *Y, int type, int xy_dt
         case T_Q6_K: rc = dispatch_dtype<T_Q6_K>(W, X, Y, xy_dtype, B, K, N, ws, stream); break;
         default: return 1;
     }
-    if (rc != 1 || B < 6 || ggb_current_yout()) return rc;
+    if (rc != 1 || B < 6 || ggb_current_yout() || ggb_current_xin()) return rc;
     // the B x K activation image does not fit in shared memory next to a useful ring (very long rows): two passes
     // over the weights with half the batch each still beat the dp4a kernels, which would split the batch as well.
     // The second pass's image kernel waits for the first pass's GEMV (stream order), so both can share `ws`.

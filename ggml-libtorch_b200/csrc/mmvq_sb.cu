@@ -36,6 +36,7 @@ constexpr int kBatchBlock = 4;          // batch rows processed per pass over an
 struct SbParams {
     const uint8_t *W;
     const void *X;
+    GgbXIn xin;
     GgbYOut yo;
     int64_t N;
     int K;
@@ -506,7 +507,7 @@ mmvq_sb_kernel(const SbParams p) {
                 const int gi = base + u * GPI + (tid >> 2);
                 if (gi < total) {
                     const int b = (B == 1) ? 0 : gi / ngroups_row, g = gi - b * ngroups_row;
-                    load8_f32<T>(X + (int64_t)b * K + g * 32 + t4 * 8, p.x_vec != 0, v[u]);
+                    load_act8<T>(X, static_cast<const T *>(p.xin.x2), p.xin.ldx, b, g * 32 + t4 * 8, p.x_vec != 0, v[u]);
                 } else {
 #pragma unroll
                     for (int i = 0; i < 8; i++) v[u][i] = 0.0f;
@@ -642,7 +643,9 @@ int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, cudaStre
         p.chunk_stride = 16 * Ops::BS;                          // multiple of 16 for every type (BS is even)
         p.slot_stride = (2 * p.chunk_stride + 127) & ~127;
     }
-    p.x_vec = (reinterpret_cast<uintptr_t>(X) & 15) == 0;
+    p.xin = ggb_make_xin(K);
+    p.x_vec = (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.xin.x2) & 15) == 0 &&
+              (p.xin.ldx * (int64_t)sizeof(T)) % 16 == 0;
     p.pdl_prefetch = g_pdl_prefetch;
     p.trace = ggb_mmvq_trace_slot();
     const int act_q = (int)(B * K);

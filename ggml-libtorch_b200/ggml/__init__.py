@@ -22,7 +22,7 @@ from ._capi import (GGB_BF16, GGB_F16, GGB_F32, GGB_OPT_STATIC_WEIGHTS, GGB_Q8_1
 __all__ = [
     "ggml_dequantize", "ggml_mul_mat_vec_a8", "ggml_mul_mat_a8", "ggml_quantize_q8_1",
     "dequantize_out", "mul_mat_vec_a8_out", "mul_mat_a8_out", "mmq_workspace_bytes", "mmvq_workspace_bytes",
-    "set_option", "GGB_OPT_STATIC_WEIGHTS", "mul_mat_vec_a8_gather",
+    "set_option", "GGB_OPT_STATIC_WEIGHTS", "mul_mat_vec_a8_gather", "mul_mat_vec_a8_fused",
     "block_elems", "block_bytes", "SUPPORTED_TYPES", "MMVQ_MAX_BATCH",
 ]
 
@@ -160,6 +160,35 @@ def mul_mat_vec_a8_gather(W: torch.Tensor, X: torch.Tensor, quant_type: int, row
                                   int(ldy), int(col_offset), ws.data_ptr() if ws is not None else None,
                                   ws.numel() * ws.element_size() if ws is not None else 0, _stream(W))
     _capi.check(rc, "ggml_mul_mat_vec_a8 (gather)")
+
+
+def mul_mat_vec_a8_fused(W: torch.Tensor, X: torch.Tensor, X2: torch.Tensor | None, quant_type: int, row: int, peer_ptrs,
+                         ldy: int, col_offset: int, split_row: int = 0, col_offset2: int = 0,
+                         ws: torch.Tensor | None = None) -> None:
+    """The general fused MMVQ (ggb_mmvq_fused).  X (and X2) are [B, K] views with unit column stride and a common row
+    stride; with X2 the activation is silu(X) * X2 computed on the fly (torch eager's roundings).  Results go to
+    `peer_ptrs[i] + (tok * ldy + col) * itemsize` with col = col_offset + r for r < split_row (or no split), else
+    col_offset2 + r - split_row."""
+    what = "ggml_mul_mat_vec_a8 (fused)"
+    if not X.is_cuda or X.device != W.device or X.dtype not in _DT or X.dim() != 2 or X.stride(1) != 1:
+        raise ValueError(f"{what}: X must be a CUDA [B, K] view with unit column stride on W's device (fp32/fp16/bf16)")
+    if X2 is not None and (X2.shape != X.shape or X2.dtype != X.dtype or X2.stride() != X.stride() or X2.device != X.device):
+        raise ValueError(f"{what}: X2 must match X in shape, dtype, strides and device")
+    B, K = X.shape
+    if not 1 <= B <= MMVQ_MAX_BATCH:
+        raise ValueError(f"{what}: batch {B} outside 1..{MMVQ_MAX_BATCH}")
+    _check_w(W, quant_type, row, K, what)
+    import ctypes
+    need = mmvq_workspace_bytes(quant_type, B, K, row)
+    if need and (ws is None or ws.numel() * ws.element_size() < need):
+        ws = torch.empty(need, dtype=torch.uint8, device=W.device)
+    arr = (ctypes.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+    with torch.cuda.device(W.device):
+        rc = _lib.ggb_mmvq_fused(W.data_ptr(), X.data_ptr(), X2.data_ptr() if X2 is not None else None, X.stride(0),
+                                 int(quant_type), _DT[X.dtype], B, K, row, arr, len(peer_ptrs), int(ldy), int(col_offset),
+                                 int(split_row), int(col_offset2), ws.data_ptr() if ws is not None else None,
+                                 ws.numel() * ws.element_size() if ws is not None else 0, _stream(W))
+    _capi.check(rc, what)
 
 
 def mmq_workspace_bytes(quant_type: int, M: int, K: int, N: int) -> int:

@@ -19,7 +19,7 @@ GGB_OPT_STATIC_WEIGHTS = 1
 SYMBOLS = (
     "ggb_version", "ggb_last_error", "ggb_set_option", "ggb_block_elems", "ggb_block_bytes",
     "ggb_dequantize", "ggb_q8_1_bytes", "ggb_quantize_q8_1",
-    "ggb_mmvq_workspace_bytes", "ggb_mmvq", "ggb_mmvq_gather", "ggb_mmq_workspace_bytes", "ggb_mmq",
+    "ggb_mmvq_workspace_bytes", "ggb_mmvq", "ggb_mmvq_gather", "ggb_mmvq_fused", "ggb_mmq_workspace_bytes", "ggb_mmq",
 )
 
 
@@ -48,6 +48,7 @@ def _load() -> ctypes.CDLL:
     L.ggb_mmvq_workspace_bytes.restype = i64
     L.ggb_mmvq.argtypes = [vp, vp, vp, ci, ci, i64, i64, i64, vp, i64, vp]
     L.ggb_mmvq_gather.argtypes = [vp, vp, ci, ci, i64, i64, i64, ctypes.POINTER(vp), ci, i64, i64, vp, i64, vp]
+    L.ggb_mmvq_fused.argtypes = [vp, vp, vp, i64, ci, ci, i64, i64, i64, ctypes.POINTER(vp), ci, i64, i64, i64, i64, vp, i64, vp]
     L.ggb_mmq_workspace_bytes.argtypes = [ci, i64, i64, i64]
     L.ggb_mmq_workspace_bytes.restype = i64
     L.ggb_mmq.argtypes = [vp, vp, vp, ci, ci, i64, i64, i64, i64, vp, i64, vp]

@@ -129,7 +129,7 @@ class ColumnParallelQuantLinear:
 
 class QuantMLP:
     """Llama-style MLP block on column-parallel quantized weights (BASELINE configs[4]):
-    down( silu(gate(x)) * up(x) ), each projection sharded along its N with an all-gather of its output."""
+    down( silu(gate(x)) * up(x) ), each projection sharded along its N with an exchange of its output."""
 
     def __init__(self, gate: ColumnParallelQuantLinear, up: ColumnParallelQuantLinear, down: ColumnParallelQuantLinear):
         self.gate, self.up, self.down = gate, up, down
@@ -139,5 +139,77 @@ class QuantMLP:
         u = self.up(X)
         h = torch.nn.functional.silu(g) * u
         return self.down(h)
+
+    __call__ = forward
+
+
+class FusedQuantMLP:
+    """The same block for decode batches (M <= 8, K-quants) as TWO launches and two barriers:
+
+      1. one MMVQ over the stacked shard [gate_shard; up_shard]: its epilogue writes the gate slice and the up slice of
+         a symmetric [8, 2 * I] buffer on every rank (ggb_mmvq_fused with split output columns);
+      2. the down projection reads g = buf[:, :I], u = buf[:, I:] and computes silu(g) * u inside its activation
+         quantization, then gathers its own output the same way.
+
+    The result equals QuantMLP's bit for bit: rows are independent of how many share a launch, and the SwiGLU is
+    computed with torch eager's roundings.  Larger batches / other types fall back to QuantMLP's path."""
+
+    def __init__(self, gate: ColumnParallelQuantLinear, up: ColumnParallelQuantLinear, down: ColumnParallelQuantLinear):
+        if gate.quant_type != up.quant_type or gate.n_total != up.n_total or gate.W.shape[1] != up.W.shape[1]:
+            raise ValueError("gate and up must share type and shape")
+        self.plain = QuantMLP(gate, up, down)
+        self.gate, self.up, self.down = gate, up, down
+        self.rank, self.world, self.group = gate.rank, gate.world, gate.group
+        self.W_gu = torch.cat([gate.W, up.W], dim=0).contiguous()        # [2 * I / tp, row_bytes]
+        self.inter, self.hidden = gate.n_total, down.n_total
+        self._bufs = {}
+        self._calls = 0
+        self._ws = None
+        self.fused = True
+
+    def _buffers(self, dtype, device):
+        """per dtype: two (gate|up buffer, down buffer) pairs, each with its peer pointers and barrier handle"""
+        if dtype not in self._bufs:
+            from . import MMVQ_MAX_BATCH
+            sets = []
+            for _ in range(2):
+                pair = []
+                for cols in (2 * self.inter, self.hidden):
+                    if self.world > 1:
+                        import torch.distributed._symmetric_memory as symm_mem
+                        buf = symm_mem.empty((MMVQ_MAX_BATCH, cols), dtype=dtype, device=device)
+                        hdl = symm_mem.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+                        pair.append((buf, hdl, [int(p) for p in hdl.buffer_ptrs]))
+                    else:
+                        buf = torch.empty((MMVQ_MAX_BATCH, cols), dtype=dtype, device=device)
+                        pair.append((buf, None, [buf.data_ptr()]))
+                sets.append(pair)
+            self._bufs[dtype] = sets
+        return self._bufs[dtype]
+
+    def forward(self, X: torch.Tensor) -> torch.Tensor:
+        if not (self.fused and X.dim() == 2 and X.shape[0] <= 8):
+            return self.plain(X)
+        from . import mmvq_workspace_bytes, mul_mat_vec_a8_fused
+        M, K = X.shape
+        (gu, gu_h, gu_p), (dn, dn_h, dn_p) = self._buffers(X.dtype, X.device)[self._calls & 1]
+        n_gu, n_dn, I = self.gate.n_local, self.down.n_local, self.inter
+        need = max(mmvq_workspace_bytes(self.gate.quant_type, M, K, 2 * n_gu), mmvq_workspace_bytes(self.down.quant_type, M, I, n_dn))
+        if need and (self._ws is None or self._ws.numel() < need):
+            self._ws = torch.empty(need, dtype=torch.uint8, device=X.device)
+        try:
+            mul_mat_vec_a8_fused(self.W_gu, X, None, self.gate.quant_type, 2 * n_gu, gu_p, 2 * I, self.rank * n_gu,
+                                 n_gu, I + self.rank * n_gu, self._ws)
+        except ValueError:
+            self.fused = False                   # not on the fused path (same verdict on every rank, nothing launched)
+            return self.plain(X)
+        if gu_h is not None:
+            gu_h.barrier(channel=0)
+        mul_mat_vec_a8_fused(self.down.W, gu[:M, :I], gu[:M, I:], self.down.quant_type, n_dn, dn_p, self.hidden,
+                             self.rank * n_dn, 0, 0, self._ws)
+        if dn_h is not None:
+            dn_h.barrier(channel=0)
+        self._calls += 1
+        return dn[:M]
 
     __call__ = forward

@@ -118,6 +118,21 @@ int         ggb_mmvq_gather(const void *W, const void *X, int type, int xy_dtype
                             void *ws, int64_t ws_bytes, void *stream);
 
 /*
+ * The general form (the Llama MLP block on quantized weights as two launches).
+ *   activation:  X [B, K] with row stride ldx (elements).  X2 != NULL: the activation is silu(X) * X2, computed on the fly
+ *                with torch eager's roundings (silu and the product each rounded to the tensor dtype), so a down
+ *                projection fed by the gate and up outputs equals ggb_mmvq(W, F.silu(g) * u) bit for bit.
+ *   output:      as ggb_mmvq_gather; with 0 < split_row < N, rows >= split_row go to column col_offset2 + (row -
+ *                split_row): W = [gate_shard; up_shard] stacked writes the gate slice and the up slice of one
+ *                [B, 2 * N_total] buffer in ONE launch.
+ * Same types / shapes as ggb_mmvq_gather.
+ */
+int         ggb_mmvq_fused(const void *W, const void *X, const void *X2, int64_t ldx, int type, int xy_dtype,
+                           int64_t B, int64_t K, int64_t N, void *const *y_peers, int n_peers, int64_t ldy,
+                           int64_t col_offset, int64_t split_row, int64_t col_offset2,
+                           void *ws, int64_t ws_bytes, void *stream);
+
+/*
  * MMQ: Y[M, N] (row stride ldy elements) = q8_1_mmq(X[M, K]) . W[N, K]^T.
  * Replaces ggml_mul_mat_a8 (ggml/mmq.cu:180-255): quantize_mmq_q8_1_cuda + mul_mat_q
  * (ggml/mmq.cuh:1917-2031).  `ws` must hold ggb_mmq_workspace_bytes(...) bytes (the quantized

@@ -122,6 +122,34 @@ def test_gather_epilogue_single_gpu(ops, case):
         ops.mul_mat_vec_a8_gather(w8, x[:, :256].contiguous(), oracle.Q8_0, 8, [bufs[0].data_ptr()], ld, 0)
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32], ids=["f16", "bf16", "f32"])
+def test_fused_swiglu_mlp_block_single_gpu(ops, dtype):
+    """the MLP block as two launches (stacked gate|up with split output columns, then a down
+    projection that computes silu(g) * u inside its activation quantization) equals the three-matmul + eager
+    SwiGLU path bit for bit, for every decode batch."""
+    from ggml.parallel import ColumnParallelQuantLinear, FusedQuantMLP, QuantMLP
+    hidden, inter = 2048, 4096
+    dev = torch.device("cuda")
+    mk = lambda t, n, k, seed: ColumnParallelQuantLinear(torch.from_numpy(oracle.random_weights(t, n, k, seed=seed)).to(dev), t, n, 0, 1)
+    gate, up, down = mk(oracle.Q4_K, inter, hidden, 1), mk(oracle.Q4_K, inter, hidden, 2), mk(oracle.Q6_K, hidden, inter, 3)
+    plain, fused = QuantMLP(gate, up, down), FusedQuantMLP(gate, up, down)
+    for M in (1, 2, 3, 5, 8):
+        x = (torch.randn(M, hidden, generator=torch.Generator().manual_seed(M)) * 0.25).to(dtype).to(dev)
+        want = plain(x)
+        for _ in range(2):                                  # both buffer sets
+            got = fused(x)
+            assert got.shape == want.shape and got.dtype == want.dtype
+            assert torch.equal(got, want), f"M={M} {dtype}: max diff {(got.float() - want.float()).abs().max().item()}"
+    assert fused.fused, "the fused path fell back"
+    # the SwiGLU activation alone, against the oracle on silu(g) * u computed by torch
+    g = torch.randn(3, inter, generator=torch.Generator().manual_seed(7)).to(dtype).to(dev)
+    u = torch.randn(3, inter, generator=torch.Generator().manual_seed(8)).to(dtype).to(dev)
+    h = torch.nn.functional.silu(g) * u
+    y = torch.empty(3, hidden, dtype=dtype, device=dev)
+    ops.mul_mat_vec_a8_fused(down.W, g, u, oracle.Q6_K, hidden, [y.data_ptr()], hidden, 0)
+    assert torch.equal(y, ops.ggml_mul_mat_vec_a8(down.W, h, oracle.Q6_K, hidden))
+
+
 def test_linearity_property(ops):
     """size-independent property at full size: rows of Y are independent, so a row-slice of W gives the
     same values as the slice of the full result (bit-for-bit: same K order per row)."""

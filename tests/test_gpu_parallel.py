@@ -63,6 +63,16 @@ def _worker(rank, world, port, out_dir):
                 y = fmlp(x)
             res[f"fused{M}"] = y.float().cpu().numpy()
         res["fused_active"] = np.array([int(fmlp.gate.fused_gather), int(fmlp.down.fused_gather)])
+        # ... and the whole block as two launches (stacked gate|up, SwiGLU inside the down projection)
+        from ggml.parallel import FusedQuantMLP
+        mkp = lambda w, tt, n: ColumnParallelQuantLinear(shard_rows(w, rank, world).to(dev), tt, n, rank, world)
+        bmlp = FusedQuantMLP(mkp(wg, oracle.Q4_K, INTER), mkp(wu, oracle.Q4_K, INTER), mkp(wd, oracle.Q6_K, HIDDEN))
+        for M in BATCHES:
+            x = _inputs(M).to(dev)
+            for rep in range(3):
+                y = bmlp(x)
+            res[f"block{M}"] = y.float().cpu().numpy()
+        res["block_active"] = np.array([int(bmlp.fused)])
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), **res)
     finally:
         dist.destroy_process_group()
@@ -90,4 +100,6 @@ def test_column_parallel_world2_nccl(tmp_path):
             assert np.array_equal(r[f"gate{M}"], want_gate), f"gate M={M}: sharded != single-GPU"
             assert np.array_equal(r[f"mlp{M}"], want_mlp), f"mlp M={M}: sharded != single-GPU"
             assert np.array_equal(r[f"fused{M}"], want_mlp), f"mlp M={M}: fused gather != single-GPU"
+            assert np.array_equal(r[f"block{M}"], want_mlp), f"mlp M={M}: fused block != single-GPU"
     assert r0["fused_active"].tolist() == [1, 1], "the fused path fell back to NCCL"
+    assert r0["block_active"].tolist() == [1], "the fused block fell back"
