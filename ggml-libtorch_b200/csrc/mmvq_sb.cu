@@ -413,7 +413,7 @@ __device__ __forceinline__ void run_batches(const uint8_t *w0, const uint8_t *w1
 // ------------------------------------------------------------------------------------------------
 template <int TYPE, int B, typename T, int NW>
 __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1)
-mmvq_sb_kernel(const SbParams p) {
+mmvq_sb_kernel(const SbParams p, const int g_defer) {
     using Ops = SbOps<TYPE>;
     extern __shared__ __align__(128) uint8_t smem[];
     uint4 *act_q = reinterpret_cast<uint4 *>(smem);                            // [B][8][ipr]
@@ -545,6 +545,53 @@ mmvq_sb_kernel(const SbParams p) {
     const int pair = lane / lpp, sbl = lane - pair * lpp;          // row pair inside the slot, lane inside the pair
     int ring = ring_base;
     uint32_t phase = 0;
+    if (p.nchunks == 1 && ipr == 32 && g_defer) {
+        // Short rows (K = 4096: one slot = one row pair x all 32 items).  The lane partials of slot g are reduced and
+        // stored while slot g + 1 is being computed: the 5-step shuffle chain (~150 cycles of pure latency per slot on
+        // a warp that shares its scheduler with one other) overlaps the next slot's shared-memory loads and dp4a chains.
+        float prev[2][B];
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+#pragma unroll
+            for (int b = 0; b < B; b++) prev[r][b] = 0.0f;
+        for (int g = 0; g <= my_groups; g++) {
+            float acc[2][B];
+#pragma unroll
+            for (int r = 0; r < 2; r++)
+#pragma unroll
+                for (int b = 0; b < B; b++) acc[r][b] = 0.0f;
+            if (g < my_groups) {
+                mbar_wait(&full[ring], phase);
+                const uint8_t *w0 = slots + ring * p.slot_stride + (lane >> 1) * Ops::BS;
+                run_batches<TYPE, B, 0>(w0, w0 + p.row_bytes, lane & 1, act_q + lane, act_s + lane, ipr, acc);
+            }
+            // reduction + store of the PREVIOUS slot (g - 1): independent of everything above
+            const int lr0 = (warp + (g - 1) * wu) * 2;
+#pragma unroll
+            for (int b = 0; b < B; b++) {
+                const bool up = (lane & 16) != 0;
+                float v = (up ? prev[1][b] : prev[0][b]) + __shfl_xor_sync(0xffffffffu, up ? prev[0][b] : prev[1][b], 16);
+#pragma unroll
+                for (int m = 8; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+                const int lr = lr0 + (up ? 1 : 0);
+                if (g > 0 && (lane & 15) == 0 && lr < nrows) ggb_yout_store<T>(p.yo, b, r_begin + lr, v);
+            }
+            if (g < my_groups) {
+                __syncwarp();
+                if (lane == 0 && is_k < my_slots) {    // recycle the slot: every lane has finished reading it
+                    fence_proxy_async();
+                    issue_next();
+                }
+                if (++ring == ring_base + depth) { ring = ring_base; phase ^= 1u; }
+            }
+#pragma unroll
+            for (int r = 0; r < 2; r++)
+#pragma unroll
+                for (int b = 0; b < B; b++) prev[r][b] = acc[r][b];
+        }
+        if (p.trace && tid == 0) p.trace[blockIdx.x * 4 + 3] = gtime();
+        return;
+    }
     for (int g = 0; g < my_groups; g++) {
         float acc[2][B];
 #pragma unroll
@@ -608,6 +655,7 @@ mmvq_sb_kernel(const SbParams p) {
 int g_pdl_prefetch = 0;      // ggb_set_option(GGB_OPT_STATIC_WEIGHTS, 1)
 int g_force_warps = 0;       // tuning: 8 or 16 warps (0 = automatic)
 int g_smem_cap_kb = 0;       // tuning: dynamic shared memory budget per CTA in KB (0 = automatic)
+int g_defer_reduce = 1;      // tuning: 0 = reduce every slot right after computing it
 int g_l2_prefetch_mb = 0;    // L2 prefetch budget per launch in MB (0 = off: measured neutral on the Llama-8B shapes, +1.5 %
                              // on the 70B ones, and every thread's prefetch is a serialised uniform-datapath instruction)
 unsigned long long *g_trace = nullptr;   // debug: device buffer of 4 stamps per CTA per launch
@@ -682,7 +730,7 @@ int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, cudaStre
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmvq_sb_kernel<TYPE, B, T, NW>, p));
+    GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmvq_sb_kernel<TYPE, B, T, NW>, p, g_defer_reduce));
     return GGB_OK;
 }
 
@@ -733,6 +781,8 @@ extern "C" void ggb_debug_mmvq_trace(void *device_buffer) {      // debug only: 
 }
 void ggb_mmvq_sb_set_l2_prefetch(int mb) { g_l2_prefetch_mb = mb < 0 ? 0 : mb; }
 void ggb_mmvq_sb_tune(int warps, int smem_cap_kb) {
+    g_defer_reduce = (warps & 0x40) ? 0 : 1;
+    warps &= 0x3f;
     g_force_warps = warps;
     g_smem_cap_kb = smem_cap_kb;
 }
