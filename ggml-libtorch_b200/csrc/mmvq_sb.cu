@@ -54,6 +54,7 @@ struct SbParams {
     int x_vec;
     int pdl_prefetch;    // 1: weights are static, the producer does not wait for the previous kernel
     int l2_prefetch;     // bytes of this CTA's weight range to pull into L2 while waiting for the previous kernel
+    int staged;          // long rows, B <= 2: quantize the activations K-chunk by K-chunk around the first row group's slots
     unsigned long long *trace;   // debug: per-CTA globaltimer stamps {start, after dependency wait, first slot, end}
 };
 
@@ -493,20 +494,39 @@ mmvq_sb_kernel(const SbParams p, const int g_defer) {
     if (p.trace && tid == 0) p.trace[blockIdx.x * 4 + 1] = gtime();
 
     // ===================== q8_1-quantize the activations into shared memory =====================
-    {
-        const T *X = static_cast<const T *>(p.X);
-        const int K = p.K, ngroups_row = K >> 5;
-        const int t4 = lane & 3;
-        const int total = B * ngroups_row;
-        constexpr int GPI = (NW * 32) / 4;                        // groups per pass of the CTA
-        constexpr int U = (B <= 2) ? 4 : 2;                       // passes in flight (independent loads, interleaved math)
+    const T *X = static_cast<const T *>(p.X);
+    const int ngroups_row = p.K >> 5;
+    const int t4 = lane & 3;
+    constexpr int GPI = (NW * 32) / 4;                        // groups per pass of the CTA
+    constexpr int U = (B <= 2) ? 4 : 2;                       // passes in flight (independent loads, interleaved math)
+    // quantize + store the group `gi` of the range [g_lo, g_lo + span) x B this thread's quad owns in pass u
+    auto q_store1 = [&](float (&x)[8], int gi, int g_lo, int span) {
+        const bool live = gi < B * span;
+        const int b = (live && B > 1) ? gi / span : 0;
+        const int g = live ? g_lo + gi - b * span : 0;
+        const Q8Group q = q8_1_quantize_group<Ops::NEED_S8>(x);
+        int mine = __dp4a((int)q.q_lo, 0x01010101, __dp4a((int)q.q_hi, 0x01010101, 0));
+        mine += __shfl_xor_sync(0xffffffffu, mine, 1);                 // sum of this 16-value half
+        const int other = __shfl_xor_sync(0xffffffffu, mine, 2);
+        if (live) {
+            const int it = g >> 2, j = g & 3;                          // item, group inside the item
+            const int i = 2 * j + (t4 >> 1);                           // 16-value chunk inside the item
+            uint8_t *dst = reinterpret_cast<uint8_t *>(act_q + (b * 8 + i) * ipr + it) + 8 * (t4 & 1);
+            *reinterpret_cast<uint2 *>(dst) = make_uint2(q.q_lo, q.q_hi);
+            if (t4 == 0)
+                Ops::store_scales(act_s + (b * Ops::SCF4) * ipr + it, ipr, j, __half2float(__float2half_rn(q.d)), mine, other,
+                                  __half2float(__float2half_rn(q.sum)));
+        }
+    };
+    auto quantize_range = [&](int g_lo, int g_hi) {
+        const int span = g_hi - g_lo, total = B * span;
         for (int base = 0; base < total; base += U * GPI) {
             float v[U][8];
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 const int gi = base + u * GPI + (tid >> 2);
                 if (gi < total) {
-                    const int b = (B == 1) ? 0 : gi / ngroups_row, g = gi - b * ngroups_row;
+                    const int b = (B == 1) ? 0 : gi / span, g = g_lo + gi - b * span;
                     load_act8<T>(X, static_cast<const T *>(p.xin.x2), p.xin.ldx, b, g * 32 + t4 * 8, p.x_vec != 0, v[u]);
                 } else {
 #pragma unroll
@@ -515,29 +535,18 @@ mmvq_sb_kernel(const SbParams p, const int g_defer) {
             }
 #pragma unroll
             for (int u = 0; u < U; u++) {
-                const int gi = base + u * GPI + (tid >> 2);
                 if (base + u * GPI >= total) break;               // warp-uniform
-                const bool live = gi < total;
-                const int b = (live && B > 1) ? gi / ngroups_row : 0;
-                const int g = live ? gi - b * ngroups_row : 0;
-                const Q8Group q = q8_1_quantize_group<Ops::NEED_S8>(v[u]);
-                int mine = __dp4a((int)q.q_lo, 0x01010101, __dp4a((int)q.q_hi, 0x01010101, 0));
-                mine += __shfl_xor_sync(0xffffffffu, mine, 1);                 // sum of this 16-value half
-                const int other = __shfl_xor_sync(0xffffffffu, mine, 2);
-                if (live) {
-                    const int it = g >> 2, j = g & 3;                          // item, group inside the item
-                    const int i = 2 * j + (t4 >> 1);                           // 16-value chunk inside the item
-                    uint8_t *dst = reinterpret_cast<uint8_t *>(act_q + (b * 8 + i) * ipr + it) + 8 * (t4 & 1);
-                    *reinterpret_cast<uint2 *>(dst) = make_uint2(q.q_lo, q.q_hi);
-                    if (t4 == 0)
-                        Ops::store_scales(act_s + (b * Ops::SCF4) * ipr + it, ipr, j,
-                                          __half2float(__float2half_rn(q.d)), mine, other,
-                                          __half2float(__float2half_rn(q.sum)));
-                }
+                q_store1(v[u], base + u * GPI + (tid >> 2), g_lo, span);
             }
         }
-        __syncthreads();
-    }
+    };
+    // Long rows, small batches: only the first K-chunk (32 items = 128 groups) is quantized up front; chunk c + 1 is
+    // loaded before and quantized after this warp's slot of chunk c of its FIRST row group (below), so 0.9 us instead
+    // of 3.3 us of quantization (K = 14336) sit in front of the weight stream.
+    constexpr int kChunkGroups = 128;
+    const bool staged = p.staged != 0;
+    quantize_range(0, staged ? min(kChunkGroups, ngroups_row) : ngroups_row);
+    __syncthreads();
     if (p.trace && tid == 0) p.trace[blockIdx.x * 4 + 2] = gtime();
 
     // ===================== one slot = this warp's next row group x chunk =====================
@@ -592,36 +601,30 @@ mmvq_sb_kernel(const SbParams p, const int g_defer) {
         if (p.trace && tid == 0) p.trace[blockIdx.x * 4 + 3] = gtime();
         return;
     }
-    for (int g = 0; g < my_groups; g++) {
-        float acc[2][B];
-#pragma unroll
-        for (int r = 0; r < 2; r++)
-#pragma unroll
-            for (int b = 0; b < B; b++) acc[r][b] = 0.0f;
-
-        for (int c = 0; c < p.nchunks; c++) {
-            mbar_wait(&full[ring], phase);
-            const int it = c * 32 + sbl;
-            if (it < ipr) {
-                const uint8_t *w0, *w1;
-                if (p.nchunks == 1) {
-                    w0 = slots + ring * p.slot_stride + (2 * pair) * p.row_bytes + (it >> 1) * Ops::BS;
-                    w1 = w0 + p.row_bytes;
-                } else {
-                    w0 = slots + ring * p.slot_stride + (sbl >> 1) * Ops::BS;
-                    w1 = w0 + p.chunk_stride;
-                }
-                run_batches<TYPE, B, 0>(w0, w1, it & 1, act_q + it, act_s + it, ipr, acc);
+    // one slot: chunk c of the current row group
+    auto consume_slot = [&](int c, float (&acc)[2][B]) {
+        mbar_wait(&full[ring], phase);
+        const int it = c * 32 + sbl;
+        if (it < ipr) {
+            const uint8_t *w0, *w1;
+            if (p.nchunks == 1) {
+                w0 = slots + ring * p.slot_stride + (2 * pair) * p.row_bytes + (it >> 1) * Ops::BS;
+                w1 = w0 + p.row_bytes;
+            } else {
+                w0 = slots + ring * p.slot_stride + (sbl >> 1) * Ops::BS;
+                w1 = w0 + p.chunk_stride;
             }
-            __syncwarp();
-            if (lane == 0 && is_k < my_slots) {        // recycle the slot: every lane has finished reading it
-                fence_proxy_async();
-                issue_next();
-            }
-            if (++ring == ring_base + depth) { ring = ring_base; phase ^= 1u; }
+            run_batches<TYPE, B, 0>(w0, w1, it & 1, act_q + it, act_s + it, ipr, acc);
         }
-
-        // reduce over the lanes of each row pair; the first lane of the pair stores
+        __syncwarp();
+        if (lane == 0 && is_k < my_slots) {        // recycle the slot: every lane has finished reading it
+            fence_proxy_async();
+            issue_next();
+        }
+        if (++ring == ring_base + depth) { ring = ring_base; phase ^= 1u; }
+    };
+    // reduce over the lanes of each row pair; the first lane of the pair stores
+    auto finish_group = [&](int g, float (&acc)[2][B]) {
         const int lr0 = (warp + g * wu) * p.rows_per_slot + 2 * pair;
         if (lpp == 32) {
             // both rows at once: lanes 0-15 end up with row 0, lanes 16-31 with row 1
@@ -645,6 +648,69 @@ mmvq_sb_kernel(const SbParams p, const int g_defer) {
                 }
             }
         }
+    };
+
+    int g_first = 0;
+    if (staged) {
+        // every warp walks the chunks (the quantization and its barriers are CTA-wide); warps that own a row group
+        // consume its slots in between
+        constexpr int UC = (B * kChunkGroups + GPI - 1) / GPI;    // passes of the CTA that cover one chunk of every batch row
+        static_assert(B > 2 || UC <= 4, "a K-chunk of the activations is a few passes");
+        float acc[2][B];
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+#pragma unroll
+            for (int b = 0; b < B; b++) acc[r][b] = 0.0f;
+        for (int c = 0; c < p.nchunks; c++) {
+            const int g_lo = (c + 1) * kChunkGroups, span = min(kChunkGroups, ngroups_row - g_lo);
+            const bool more = c + 1 < p.nchunks;
+            // chunk c + 1 of X, kept in its storage type while it waits (4 registers per 8 fp16 / bf16 values)
+            uint4 raw[UC][sizeof(T) == 4 ? 2 : 1];
+            if (more) {
+#pragma unroll
+                for (int u = 0; u < UC; u++) {
+                    const int gi = u * GPI + (tid >> 2);
+#pragma unroll
+                    for (int h = 0; h < (sizeof(T) == 4 ? 2 : 1); h++) raw[u][h] = make_uint4(0, 0, 0, 0);
+                    if (gi < B * span) {
+                        const int b = (B == 1) ? 0 : gi / span, g = g_lo + gi - b * span;
+                        const T *src = X + (int64_t)b * p.xin.ldx + g * 32 + t4 * 8;
+                        raw[u][0] = *reinterpret_cast<const uint4 *>(src);                 // staged mode requires x_vec
+                        if (sizeof(T) == 4) raw[u][sizeof(T) == 4 ? 1 : 0] = *reinterpret_cast<const uint4 *>(src + 4);
+                    }
+                }
+            }
+            if (my_groups > 0) consume_slot(c, acc);
+            if (more) {
+#pragma unroll
+                for (int u = 0; u < UC; u++) {
+                    if (u * GPI >= B * span) break;               // warp-uniform
+                    float x[8];
+                    if constexpr (sizeof(T) == 4) {
+                        const float *f = reinterpret_cast<const float *>(&raw[u][0]);
+#pragma unroll
+                        for (int i = 0; i < 8; i++) x[i] = f[i];
+                    } else {
+                        const T *h = reinterpret_cast<const T *>(&raw[u][0]);
+#pragma unroll
+                        for (int i = 0; i < 8; i++) x[i] = to_f32<T>(h[i]);
+                    }
+                    q_store1(x, u * GPI + (tid >> 2), g_lo, span);
+                }
+                __syncthreads();
+            }
+        }
+        if (my_groups > 0) finish_group(0, acc);
+        g_first = 1;
+    }
+    for (int g = g_first; g < my_groups; g++) {
+        float acc[2][B];
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+#pragma unroll
+            for (int b = 0; b < B; b++) acc[r][b] = 0.0f;
+        for (int c = 0; c < p.nchunks; c++) consume_slot(c, acc);
+        finish_group(g, acc);
     }
     if (p.trace && tid == 0) p.trace[blockIdx.x * 4 + 3] = gtime();
 }
@@ -655,6 +721,7 @@ mmvq_sb_kernel(const SbParams p, const int g_defer) {
 int g_pdl_prefetch = 0;      // ggb_set_option(GGB_OPT_STATIC_WEIGHTS, 1)
 int g_force_warps = 0;       // tuning: 8 or 16 warps (0 = automatic)
 int g_smem_cap_kb = 0;       // tuning: dynamic shared memory budget per CTA in KB (0 = automatic)
+int g_staged = 1;            // tuning: 0 = quantize the whole activation row(s) up front
 int g_defer_reduce = 1;      // tuning: 0 = reduce every slot right after computing it
 int g_l2_prefetch_mb = 0;    // L2 prefetch budget per launch in MB (0 = off: measured neutral on the Llama-8B shapes, +1.5 %
                              // on the 70B ones, and every thread's prefetch is a serialised uniform-datapath instruction)
@@ -694,6 +761,9 @@ int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, cudaStre
     p.xin = ggb_make_xin(K);
     p.x_vec = (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.xin.x2) & 15) == 0 &&
               (p.xin.ldx * (int64_t)sizeof(T)) % 16 == 0;
+    // measured (same box, vs quantizing everything up front): Q4_K +3.4 % at K = 14336 and 28672, Q6_K +2.3 % at 14336 but
+    // -7.7 % at 28672 (six CTA-wide barriers around heavier slots)
+    p.staged = (p.nchunks > 1 && (TYPE != T_Q6_K || p.nchunks <= 4) && B <= 2 && g_staged && p.x_vec && p.xin.x2 == nullptr) ? 1 : 0;
     p.pdl_prefetch = g_pdl_prefetch;
     p.trace = ggb_mmvq_trace_slot();
     const int act_q = (int)(B * K);
@@ -782,6 +852,8 @@ extern "C" void ggb_debug_mmvq_trace(void *device_buffer) {      // debug only: 
 void ggb_mmvq_sb_set_l2_prefetch(int mb) { g_l2_prefetch_mb = mb < 0 ? 0 : mb; }
 void ggb_mmvq_sb_tune(int warps, int smem_cap_kb) {
     g_defer_reduce = (warps & 0x40) ? 0 : 1;
+    g_staged = (warps & 0x80) ? 0 : 1;
+    warps &= ~0x80;
     warps &= 0x3f;
     g_force_warps = warps;
     g_smem_cap_kb = smem_cap_kb;
