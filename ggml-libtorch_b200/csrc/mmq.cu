@@ -92,6 +92,35 @@ __device__ __forceinline__ void bulk_g2s_mc(void *smem_dst, const void *gsrc, ui
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
         ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "h"(mask) : "memory");
 }
+// cta_group::2 (CTA pair) variants: ONE instruction issued by the leader CTA drives the tensor cores of both SMs on a
+// 256-row tile; each CTA supplies its own 128 rows of A and HALF of B, so the shared-memory traffic per MMA drops from
+// 12 KB to 8 KB per SM and the B stage from 64 KB to 32 KB
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t cta) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {      // sees arrivals from the peer CTA
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -167,10 +196,13 @@ quantize_b_image_kernel(const T *__restrict__ x, uint8_t *__restrict__ img, int6
 // CL = thread-block cluster size (1 or 2).  The CTAs of a cluster work on CL adjacent 128-row blocks of the SAME
 // token group in lock step: each CTA fetches 1/CL of every B stage and multicasts it to all of them, so the
 // L2 -> SM traffic of the B operand (the limiter at 128 rows per tile) drops by CL.
-template <int TYPE, int BN, int NB, int CL, typename T>
+// PAIR (CL == 2 only) = the two CTAs of the cluster issue ONE cta_group::2 MMA per step (see umma_f16_pair) instead of
+// two independent ones with a multicast B stage.
+template <int TYPE, int BN, int NB, int CL, typename T, bool PAIR = false>
 __global__ void __launch_bounds__(kThreads, 1)
 mmq_kernel(const Params p, const __grid_constant__ CUtensorMap tmapW) {
-    constexpr int NSTAGE = nstage_of(NB);
+    static_assert(!PAIR || CL == 2, "a CTA pair is a cluster of two");
+    constexpr int NSTAGE = PAIR ? 3 : nstage_of(NB);
     constexpr uint16_t CL_MASK = (uint16_t)((1u << CL) - 1u);
     constexpr int NACC = (NB == 1) ? 2 : 1;                   // accumulator sets in TMEM
     constexpr int QK = BlockTraits<TYPE>::QK, BS = BlockTraits<TYPE>::BS;
@@ -178,10 +210,11 @@ mmq_kernel(const Params p, const __grid_constant__ CUtensorMap tmapW) {
     // TMA box width in bytes (also the raw row slot).  The box must START on a 16-byte boundary, so for block sizes
     // that are not multiples of 16 (Q2_K 84, Q3_K 110, Q6_K 210) it starts up to 14 bytes early.
     constexpr int BOX_INNER = (SB_BYTES + ((SB_BYTES % 16) ? 14 : 0) + 15) & ~15;
-    constexpr int B_TILE_BYTES = BN * 128;
-    constexpr int B_STAGE_BYTES = NB * B_TILE_BYTES;
+    constexpr int B_TILE_BYTES = BN * 128;                    // one token tile of a stage in the image
+    constexpr int B_TILE_LOCAL = PAIR ? B_TILE_BYTES / 2 : B_TILE_BYTES;   // ... and the part of it this CTA holds
+    constexpr int B_STAGE_BYTES = NB * B_TILE_LOCAL;
     constexpr int ACC_COLS = (BN < 32) ? 32 : BN;             // TMEM columns per accumulator buffer
-    constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);   // f16 x f16 -> f32, K-major
+    constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((PAIR ? 2 * BM : BM) >> 4) << 24);   // f16 x f16 -> f32, K-major
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // SWIZZLE_128B operands need 1024-byte aligned tiles; the launch reserves the slack
@@ -194,7 +227,8 @@ mmq_kernel(const Params p, const __grid_constant__ CUtensorMap tmapW) {
     uint64_t *raw_full = bars, *raw_empty = bars + NRAW;
     uint64_t *a_full = bars + 2 * NRAW, *b_full = a_full + NSTAGE, *ab_empty = b_full + NSTAGE;
     uint64_t *acc_full = ab_empty + NSTAGE, *acc_empty = acc_full + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+    uint64_t *peer_full = acc_empty + 2;                       // PAIR, leader only: the peer CTA's A and B of a stage are in place
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(peer_full + NSTAGE);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_rbg = (p.n_row_blocks + CL - 1) / CL;          // row-block groups (CL row blocks each; a phantom one is all zeros)
@@ -204,13 +238,23 @@ mmq_kernel(const Params p, const __grid_constant__ CUtensorMap tmapW) {
 
     if (tid == 0) {
         for (int s = 0; s < NRAW; s++) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], kUnpackWarps); }
-        for (int s = 0; s < NSTAGE; s++) { mbar_init(&a_full[s], kUnpackWarps); mbar_init(&b_full[s], 1); mbar_init(&ab_empty[s], CL); }
-        for (int s = 0; s < 2; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }   // NB == 2 uses slot 0 only
+        for (int s = 0; s < NSTAGE; s++) {
+            mbar_init(&a_full[s], kUnpackWarps);
+            mbar_init(&b_full[s], 1);
+            mbar_init(&ab_empty[s], PAIR ? 1 : CL);            // PAIR: one multicast commit by the leader
+            mbar_init(&peer_full[s], 1);
+        }
+        for (int s = 0; s < 2; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], PAIR ? 8 : 4); }   // NB == 2 uses slot 0 only
         fence_mbar_init();
     }
     if (warp == 1) {   // TMEM: all 512 columns (two accumulator buffers); one CTA per SM so no contention
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     if (CL == 1) __syncthreads();
@@ -262,10 +306,17 @@ mmq_kernel(const Params p, const __grid_constant__ CUtensorMap tmapW) {
                         const int ks = sb * (RAWK / KSTEP) + q;
                         // the nb_valid token tiles of a group are adjacent in the image: one contiguous copy
                         const uint8_t *src = p.Ximg + ((int64_t)ks * p.img_plane + (int64_t)tt * (BN >> 3)) * 1024;
-                        mbar_expect_tx(&b_full[s], (uint32_t)(nb_valid * B_TILE_BYTES));
-                        if (CL == 1) {
+                        if (PAIR) {
+                            // this CTA's half (tokens crank * BN/2 ..) of each token tile of the stage
+                            mbar_expect_tx(&b_full[s], (uint32_t)(nb_valid * B_TILE_LOCAL));
+                            for (int tb = 0; tb < nb_valid; tb++)
+                                bulk_g2s_plain(sB + s * B_STAGE_BYTES + tb * B_TILE_LOCAL, src + tb * B_TILE_BYTES + crank * B_TILE_LOCAL,
+                                               (uint32_t)B_TILE_LOCAL, &b_full[s]);
+                        } else if (CL == 1) {
+                            mbar_expect_tx(&b_full[s], (uint32_t)(nb_valid * B_TILE_BYTES));
                             bulk_g2s_plain(sB + s * B_STAGE_BYTES, src, (uint32_t)(nb_valid * B_TILE_BYTES), &b_full[s]);
                         } else {
+                            mbar_expect_tx(&b_full[s], (uint32_t)(nb_valid * B_TILE_BYTES));
                             const uint32_t part = (uint32_t)(nb_valid * B_TILE_BYTES) / CL;
                             bulk_g2s_mc(sB + s * B_STAGE_BYTES + crank * part, src + crank * part, part, &b_full[s], CL_MASK);
                         }
@@ -278,12 +329,25 @@ mmq_kernel(const Params p, const __grid_constant__ CUtensorMap tmapW) {
         else if (p.pdl == 0 && lane == 0) ggb_pdl_launch_dependents();
     } else if (warp == 1) {
         // ============================ MMA issuer (one thread) ============================
-        if (lane == 0) {
+        if (lane == 0 && PAIR && crank != 0) {
+            // peer CTA of a pair: no MMA to issue; relay "my A tile and my half of B for stage s are in place" to the leader
+            int it = 0;
+            for (int tile = cid; tile < ntiles; tile += ncl) {
+                for (int ks = 0; ks < ksteps_total; ks++, it++) {
+                    const int s = it % NSTAGE;
+                    const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u;
+                    mbar_wait(&a_full[s], ph);
+                    mbar_wait(&b_full[s], ph);
+                    mbar_arrive_remote(&peer_full[s], 0);
+                }
+            }
+        } else if (lane == 0) {
             int it = 0, tcount = 0;
             for (int tile = cid; tile < ntiles; tile += ncl, tcount++) {
                 const int ab = tcount % NACC;
                 const int nb_valid = min(NB, p.n_tok_tiles - (tile / n_rbg) * NB);
-                mbar_wait(&acc_empty[ab], ((uint32_t)(tcount / NACC) & 1u) ^ 1u);
+                if (PAIR) mbar_wait_cluster(&acc_empty[ab], ((uint32_t)(tcount / NACC) & 1u) ^ 1u);   // both CTAs' epilogues
+                else mbar_wait(&acc_empty[ab], ((uint32_t)(tcount / NACC) & 1u) ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(ab * ACC_COLS);
                 for (int ks = 0; ks < ksteps_total; ks++, it++) {
@@ -291,21 +355,32 @@ mmq_kernel(const Params p, const __grid_constant__ CUtensorMap tmapW) {
                     const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u;
                     mbar_wait(&a_full[s], ph);
                     mbar_wait(&b_full[s], ph);
+                    if (PAIR) mbar_wait_cluster(&peer_full[s], ph);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(sA + s * A_STAGE_BYTES);
                     const uint32_t b_addr = smem_u32(sB + s * B_STAGE_BYTES);
 #pragma unroll
                     for (int kk = 0; kk < KSTEP / 16; kk++) {
-                        umma_f16(d_tmem, umma_desc_sw128(a_addr + kk * 32), umma_desc_sw128(b_addr + kk * 32), IDESC,
-                                 (ks > 0 || kk > 0) ? 1u : 0u);
-                        if (NB == 2 && nb_valid == 2)
-                            umma_f16(d_tmem + ACC_COLS, umma_desc_sw128(a_addr + kk * 32),
-                                     umma_desc_sw128(b_addr + B_TILE_BYTES + kk * 32), IDESC, (ks > 0 || kk > 0) ? 1u : 0u);
+                        const uint32_t acc = (ks > 0 || kk > 0) ? 1u : 0u;
+                        if (PAIR) {
+                            // 256 weight rows (128 per CTA) x BN tokens (BN / 2 rows of B from each CTA's shared memory)
+                            umma_f16_pair(d_tmem, umma_desc_sw128(a_addr + kk * 32), umma_desc_sw128(b_addr + kk * 32), IDESC, acc);
+                            if (NB == 2 && nb_valid == 2)
+                                umma_f16_pair(d_tmem + ACC_COLS, umma_desc_sw128(a_addr + kk * 32),
+                                              umma_desc_sw128(b_addr + B_TILE_LOCAL + kk * 32), IDESC, acc);
+                        } else {
+                            umma_f16(d_tmem, umma_desc_sw128(a_addr + kk * 32), umma_desc_sw128(b_addr + kk * 32), IDESC, acc);
+                            if (NB == 2 && nb_valid == 2)
+                                umma_f16(d_tmem + ACC_COLS, umma_desc_sw128(a_addr + kk * 32),
+                                         umma_desc_sw128(b_addr + B_TILE_BYTES + kk * 32), IDESC, acc);
+                        }
                     }
-                    if (CL == 1) umma_commit(&ab_empty[s]);    // frees the A/B stage when these MMAs retire
-                    else umma_commit_mc(&ab_empty[s], CL_MASK); // ... in every CTA of the cluster (they multicast into it)
+                    if (PAIR) umma_commit_pair(&ab_empty[s], CL_MASK);       // frees the stage in both CTAs
+                    else if (CL == 1) umma_commit(&ab_empty[s]);              // frees the A/B stage when these MMAs retire
+                    else umma_commit_mc(&ab_empty[s], CL_MASK);               // ... in every CTA of the cluster (they multicast into it)
                 }
-                umma_commit(&acc_full[ab]);                    // accumulator complete
+                if (PAIR) umma_commit_pair(&acc_full[ab], CL_MASK);          // accumulators complete in both CTAs
+                else umma_commit(&acc_full[ab]);
             }
         }
         __syncwarp();
@@ -367,7 +442,10 @@ mmq_kernel(const Params p, const __grid_constant__ CUtensorMap tmapW) {
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[ab]);
+            if (lane == 0) {
+                if (PAIR && crank != 0) mbar_arrive_remote(&acc_empty[ab], 0);     // the leader issues the next tile's MMAs
+                else mbar_arrive(&acc_empty[ab]);
+            }
         }
     } else {
         // ============================ unpack warps: raw GGUF bytes -> fp16 swizzled A tile ============================
@@ -452,12 +530,13 @@ mmq_kernel(const Params p, const __grid_constant__ CUtensorMap tmapW) {
     else cluster_sync_all();                                   // no CTA leaves while a peer may still signal or copy into it
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
     }
 }
 
 // ---------------------------------------------------------------- host side
-int g_mmq_cfg = 0;           // tuning bits: 1 = one token tile per weight stage, 2 = no clusters (0 = automatic)
+int g_mmq_cfg = 0;           // tuning bits: 1 = one token tile per weight stage, 2 = no clusters, 4 = no tail launch, 8 = no CTA-pair MMA
 int pick_bn(int64_t M) {
     if (M > 128) return 256;
     if (M > 64) return 128;
@@ -511,10 +590,10 @@ EncodeTiledFn get_encode_fn() {
 // returns 1 when the configuration does not fit in shared memory (the caller tries the next one)
 // img_plane = token atoms per K-plane of the image (0: this problem's own padded M); tile_limit = cluster-level tiles to
 // run (-1: all)
-template <int TYPE, int BN, int NB, int CL, typename T>
+template <int TYPE, int BN, int NB, int CL, typename T, bool PAIR = false>
 int launch_gemm(const void *W, const uint8_t *img, void *Y, int64_t M, int64_t K, int64_t N, int64_t ldy, cudaStream_t stream,
                 int img_plane = 0, int tile_limit = -1, bool is_tail = false) {
-    constexpr int NSTAGE = nstage_of(NB);
+    constexpr int NSTAGE = PAIR ? 3 : nstage_of(NB);
     constexpr int QK = BlockTraits<TYPE>::QK, BS = BlockTraits<TYPE>::BS;
     constexpr int SB_BYTES = RAWK / QK * BS;
     const DeviceInfo &di = ggb_device_info();
@@ -561,7 +640,7 @@ int launch_gemm(const void *W, const uint8_t *img, void *Y, int64_t M, int64_t K
         }
     }
     p.off_b = NSTAGE * A_STAGE_BYTES;
-    p.off_raw = p.off_b + NSTAGE * NB * BN * 128;
+    p.off_raw = p.off_b + NSTAGE * NB * BN * (PAIR ? 64 : 128);
     p.off_raw = (p.off_raw + 1023) & ~1023;
     p.off_tab = (p.off_raw + NRAW * BM * p.raw_slot + 127) & ~127;
     p.off_epi = (p.off_tab + (HalfUnpack<TYPE>::HAS ? NRAW * BM * HalfUnpack<TYPE>::NSUB * 4 : 0) + 127) & ~127;
@@ -575,7 +654,7 @@ int launch_gemm(const void *W, const uint8_t *img, void *Y, int64_t M, int64_t K
     }
     static bool attr_set[64] = {};
     if (!attr_set[di.dev]) {
-        GGB_CUDA_TRY(cudaFuncSetAttribute(mmq_kernel<TYPE, BN, NB, CL, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin));
+        GGB_CUDA_TRY(cudaFuncSetAttribute(mmq_kernel<TYPE, BN, NB, CL, T, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin));
         attr_set[di.dev] = true;
     }
     int64_t ntiles = (int64_t)((p.n_row_blocks + CL - 1) / CL) * p.n_tok_groups;             // cluster-level tiles
@@ -597,7 +676,7 @@ int launch_gemm(const void *W, const uint8_t *img, void *Y, int64_t M, int64_t K
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 2;
-    GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmq_kernel<TYPE, BN, NB, CL, T>, p, tmap));
+    GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmq_kernel<TYPE, BN, NB, CL, T, PAIR>, p, tmap));
     return GGB_OK;
 }
 
@@ -624,7 +703,8 @@ int run_typed(const void *W, const void *X, void *Y, int64_t M, int64_t K, int64
                     const int ntiles = n_rbg * n_tg, rem = ntiles % ncl;
                     const bool tail = (g_mmq_cfg & 4) == 0 && ntiles > ncl && rem > 0 && rem <= n_rbg && rem * 16 <= sms + sms / 4 &&
                                       (K % 256 == 0 || BlockTraits<TYPE>::QK == 32);
-                    rc = launch_gemm<TYPE, 256, 2, 2, T>(W, img, Y, M, K, N, ldy, stream, 0, tail ? ntiles - rem : -1);
+                    rc = (g_mmq_cfg & 8) ? launch_gemm<TYPE, 256, 2, 2, T>(W, img, Y, M, K, N, ldy, stream, 0, tail ? ntiles - rem : -1)
+                                         : launch_gemm<TYPE, 256, 2, 2, T, true>(W, img, Y, M, K, N, ldy, stream, 0, tail ? ntiles - rem : -1);
                     if (rc != 1) {
                         if (rc != GGB_OK || !tail) return rc;
                         const int64_t row0 = (int64_t)(n_rbg - rem) * 2 * BM, tok0 = (int64_t)(n_tg - 1) * 512;
