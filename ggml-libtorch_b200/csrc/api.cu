@@ -60,6 +60,8 @@ static int block_elems(int type) {
     switch (type) {
         case T_Q4_0: case T_Q4_1: case T_Q5_0: case T_Q5_1: case T_Q8_0: return 32;
         case T_Q2_K: case T_Q3_K: case T_Q4_K: case T_Q5_K: case T_Q6_K: return 256;
+        case T_IQ4_NL: return 32;
+        case T_IQ4_XS: return 256;
         default: return 0;
     }
 }
@@ -69,6 +71,7 @@ static int block_bytes(int type) {
         case T_Q5_1: return 24;  case T_Q8_0: return 34;
         case T_Q2_K: return 84;  case T_Q3_K: return 110; case T_Q4_K: return 144;
         case T_Q5_K: return 176; case T_Q6_K: return 210;
+        case T_IQ4_NL: return 18; case T_IQ4_XS: return 136;
         default: return 0;
     }
 }
@@ -289,13 +292,18 @@ int ggb_mmvq(const void *W, const void *X, void *Y, int type, int xy_dtype, int6
 }
 
 int64_t ggb_mmq_workspace_bytes(int type, int64_t M, int64_t K, int64_t N) {
-    if (block_elems(type) == 0 || M <= 0 || K <= 0 || N <= 0) return 0;
+    if (block_elems(type) == 0 || type == T_IQ4_NL || type == T_IQ4_XS || M <= 0 || K <= 0 || N <= 0) return 0;
     return ggb_mmq_workspace_bytes_impl(type, M, K, N);
 }
 
 int ggb_mmq(const void *W, const void *X, void *Y, int type, int xy_dtype, int64_t M, int64_t K, int64_t N,
             int64_t ldy, void *ws, int64_t ws_bytes, void *stream) {
     g_err[0] = 0;
+    if (type == T_IQ4_NL || type == T_IQ4_XS) {
+        // the reference's ggml_mul_mat_a8 has no case for the IQ types (mmq.cu:222-252 leaves Y uninitialised)
+        ggb_set_error("ggb_mmq: ggml type %d has dequantize and MMVQ only (no MMQ in the reference either)", type);
+        return GGB_E_TYPE;
+    }
     const int rc = check_matmul("ggb_mmq", W, X, Y, type, xy_dtype, M, K, N);
     if (rc < 0) return rc;
     if (rc > 0) return GGB_OK;

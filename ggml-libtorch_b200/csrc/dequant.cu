@@ -68,7 +68,7 @@ dequant_tile_kernel(const uint8_t *__restrict__ W, OutT *__restrict__ out, int64
     }
 
     OutT *dst = out + b0 * QK;
-    if constexpr (QK == 256) {
+    if constexpr (QK == 256 && TYPE != T_IQ4_XS) {
         // K-quants: decode every (d*sc, dmin*m) pair of the tile ONCE into a table, then one "column unit" = 8
         // consecutive bytes of a block and all the 16 / 32 values packed in them (unpack_col.cuh).
         using CU = ColUnpack<TYPE>;
@@ -93,7 +93,7 @@ dequant_tile_kernel(const uint8_t *__restrict__ W, OutT *__restrict__ out, int64
             store8(dst + ((int64_t)blk * ITEMS_PER_BLOCK + p) * 8, y);
         }
     } else {
-        // legacy types.  item = 8 consecutive values.  Thread t always handles octet p = t % ITEMS_PER_BLOCK of blocks
+        // legacy types, IQ4_NL and IQ4_XS (a warp per super-block).  item = 8 consecutive values.  Thread t always handles octet p = t % ITEMS_PER_BLOCK of blocks
         // t / ITEMS_PER_BLOCK + k * BLK_STEP, so everything derived from p (shifts, byte offsets) is loop-invariant;
         // consecutive threads write consecutive 16-byte chunks (a warp store covers 512 contiguous bytes).
         constexpr int BLK_STEP = kThreads / ITEMS_PER_BLOCK;
@@ -162,6 +162,8 @@ int ggb_dequantize_impl(const void *W, int type, int64_t nelem, void *out, int o
         case T_Q4_K: return dispatch_dtype<T_Q4_K>(W, out, nelem, out_dtype, stream);
         case T_Q5_K: return dispatch_dtype<T_Q5_K>(W, out, nelem, out_dtype, stream);
         case T_Q6_K: return dispatch_dtype<T_Q6_K>(W, out, nelem, out_dtype, stream);
+        case T_IQ4_NL: return dispatch_dtype<T_IQ4_NL>(W, out, nelem, out_dtype, stream);
+        case T_IQ4_XS: return dispatch_dtype<T_IQ4_XS>(W, out, nelem, out_dtype, stream);
         default:
             ggb_set_error("ggb_dequantize: unsupported ggml type %d", type);
             return GGB_E_TYPE;

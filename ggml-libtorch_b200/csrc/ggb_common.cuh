@@ -11,7 +11,8 @@
 // ---------------------------------------------------------------- ggml type ids (ggml-common.h:1128-1161)
 enum : int {
     T_Q4_0 = 2, T_Q4_1 = 3, T_Q5_0 = 6, T_Q5_1 = 7, T_Q8_0 = 8,
-    T_Q2_K = 10, T_Q3_K = 11, T_Q4_K = 12, T_Q5_K = 13, T_Q6_K = 14
+    T_Q2_K = 10, T_Q3_K = 11, T_Q4_K = 12, T_Q5_K = 13, T_Q6_K = 14,
+    T_IQ4_NL = 20, T_IQ4_XS = 23          // dequantize + MMVQ only, like the reference (no MMQ case: mmq.cu:222-252)
 };
 
 template <int TYPE> struct BlockTraits;
@@ -25,6 +26,8 @@ template <> struct BlockTraits<T_Q3_K> { static constexpr int QK = 256, BS = 110
 template <> struct BlockTraits<T_Q4_K> { static constexpr int QK = 256, BS = 144; };
 template <> struct BlockTraits<T_Q5_K> { static constexpr int QK = 256, BS = 176; };
 template <> struct BlockTraits<T_Q6_K> { static constexpr int QK = 256, BS = 210; };
+template <> struct BlockTraits<T_IQ4_NL> { static constexpr int QK = 32,  BS = 18;  };
+template <> struct BlockTraits<T_IQ4_XS> { static constexpr int QK = 256, BS = 136; };
 
 // ---------------------------------------------------------------- host-side error plumbing (api.cu owns the storage)
 void ggb_set_error(const char *fmt, ...);
@@ -66,6 +69,24 @@ __device__ __forceinline__ uint32_t ld_u32_a2(const uint8_t *p) {   // 2-byte al
 }
 __device__ __forceinline__ uint32_t ld_u32_a4(const uint8_t *p) {   // 4-byte aligned
     return *reinterpret_cast<const uint32_t *>(p);
+}
+
+// IQ4_NL / IQ4_XS: the 16-entry non-linear codebook (format constant kvalues_iq4nl, ggml-common.h:1060 =
+// gguf-py IQ4_NL.kvalues) as four little-endian words of int8 bytes.  `w` holds four 4-bit codes, one per byte; the
+// result holds their codebook values as int8 bytes: two PRMTs look the low 3 bits up in each table half, bit 3 selects.
+__device__ __forceinline__ uint32_t iq4nl_lut4(uint32_t w) {
+    const uint32_t s = w & 0x07070707u, t = s | (s >> 4);
+    const uint32_t sel = __byte_perm(t, 0u, 0x4420);                      // code i -> selector nibble i
+    const uint32_t lo = __byte_perm(0xBFAD9881u, 0xF6EADDCFu, sel);       // -127 -104 -83 -65 | -49 -35 -22 -10
+    const uint32_t hi = __byte_perm(0x26190D01u, 0x71594535u, sel);       //    1   13  25  38 |  53  69  89 113
+    const uint32_t m = ((w >> 3) & 0x01010101u) * 0xffu;
+    return (hi & m) | (lo & ~m);
+}
+// IQ4_XS 6-bit sub-block scale ib (0..7) with the -32 offset applied (dequantize.cuh:426-427)
+__device__ __forceinline__ int iq4xs_scale(const uint8_t *b, int ib) {
+    const int lo = (b[4 + (ib >> 1)] >> (4 * (ib & 1))) & 0x0f;
+    const int hi = (ld_u16(b + 2) >> (2 * ib)) & 3;
+    return (lo | (hi << 4)) - 32;
 }
 
 // ---------------------------------------------------------------- output conversion: ONE round-to-nearest from fp32

@@ -63,6 +63,8 @@ template <> struct VqTraits<T_Q3_K> { static constexpr bool NEED_SQ = true,  NEE
 template <> struct VqTraits<T_Q4_K> { static constexpr bool NEED_SQ = true,  NEED_S8 = false; };
 template <> struct VqTraits<T_Q5_K> { static constexpr bool NEED_SQ = true,  NEED_S8 = false; };
 template <> struct VqTraits<T_Q6_K> { static constexpr bool NEED_SQ = true,  NEED_S8 = false; };
+template <> struct VqTraits<T_IQ4_NL> { static constexpr bool NEED_SQ = false, NEED_S8 = false; };
+template <> struct VqTraits<T_IQ4_XS> { static constexpr bool NEED_SQ = false, NEED_S8 = false; };
 
 struct GroupW {
     uint32_t w[8];      // the 32 raw quants of the group, 4 per word, element order
@@ -183,6 +185,25 @@ __device__ __forceinline__ void load_group(const uint8_t *seg, int g, GroupW &o)
             const uint32_t hb = (ld_u32_a4(b + 16 + 4 * i) >> j) & 0x01010101u;
             o.w[i] = lo | (hb << 4);
         }
+    } else if constexpr (TYPE == T_IQ4_NL) {
+        const uint8_t *b = seg + g * BS;
+        o.a0 = o.a1 = ggb_h2f(ld_u16(b));
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t q = ld_u32_a2(b + 2 + 4 * i);
+            o.w[i] = iq4nl_lut4(q & 0x0f0f0f0fu);            // codebook values as int8 bytes
+            o.w[4 + i] = iq4nl_lut4((q >> 4) & 0x0f0f0f0fu);
+        }
+    } else if constexpr (TYPE == T_IQ4_XS) {
+        const uint8_t *b = seg + (g >> 3) * BS;
+        const int ib = g & 7;
+        o.a0 = o.a1 = ggb_h2f(ld_u16(b)) * (float)iq4xs_scale(b, ib);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t q = ld_u32_a4(b + 8 + 16 * ib + 4 * i);
+            o.w[i] = iq4nl_lut4(q & 0x0f0f0f0fu);
+            o.w[4 + i] = iq4nl_lut4((q >> 4) & 0x0f0f0f0fu);
+        }
     } else {   // T_Q6_K
         const uint8_t *b = seg + (g >> 3) * BS;
         const int j = g & 7, ip = j >> 2, r = j & 3;
@@ -214,7 +235,7 @@ __device__ __forceinline__ float combine(const GroupW &g, int dot0, int dot1, fl
         const float d4d8 = __half2float(__float2half_rn(g.a0 * d8));      // __hmul2(dm, ds8) in half
         const float m4s8 = __half2float(__float2half_rn(g.m0 * s8));
         return (float)(dot0 + dot1) * d4d8 + m4s8;
-    } else if constexpr (TYPE == T_Q8_0) {
+    } else if constexpr (TYPE == T_Q8_0 || TYPE == T_IQ4_NL || TYPE == T_IQ4_XS) {      // vecdotq.cuh:842-888 for the two IQ4
         return (g.a0 * d8) * (float)(dot0 + dot1);
     } else {
         const int sq0 = (int)(int16_t)(aux & 0xffffu), sq1 = (int)(int16_t)(aux >> 16);
@@ -512,6 +533,8 @@ int ggb_mmvq_impl(const void *W, const void *X, void *Y, int type, int xy_dtype,
         case T_Q4_K: return dispatch_dtype<T_Q4_K>(W, X, Y, xy_dtype, B, K, N, stream);
         case T_Q5_K: return dispatch_dtype<T_Q5_K>(W, X, Y, xy_dtype, B, K, N, stream);
         case T_Q6_K: return dispatch_dtype<T_Q6_K>(W, X, Y, xy_dtype, B, K, N, stream);
+        case T_IQ4_NL: return dispatch_dtype<T_IQ4_NL>(W, X, Y, xy_dtype, B, K, N, stream);
+        case T_IQ4_XS: return dispatch_dtype<T_IQ4_XS>(W, X, Y, xy_dtype, B, K, N, stream);
         default:
             ggb_set_error("ggb_mmvq: unsupported ggml type %d", type);
             return GGB_E_TYPE;

@@ -8,7 +8,7 @@
 //   Unpack8<TYPE>::run_sc(b, p, s, y)   the 8 values as fp32 given their pair s
 //   Unpack8<TYPE>::run(b, p, y)         = run_sc(b, p, sub_scale(b, sub_of(p)), y)
 // Arithmetic is the reference CPU op's (ggml-cpu/ggml-quants.hpp:4-112 for the legacy types, gguf-py
-// quants.py:404-572 for the K-quants): every product and sum is a separately
+// quants.py:404-572 for the K-quants, its IQ4_NL / IQ4_XS classes for those two): every product and sum is a separately
 // rounded fp32 operation (__fmul_rn / __fadd_rn / __fsub_rn are never contracted into FMA).
 // Integer quants become fp32 WITHOUT the quarter-rate I2F pipe: PRMT builds the float 2^23 + byte and
 // one exact FADD subtracts 2^23 + offset (both are integers below 2^24, so the difference is exact).
@@ -236,6 +236,40 @@ template <> struct Unpack8<T_Q6_K> {       // y = (d*sc_i8) * (q6 - 32)         
         float q[8];
         bytes_to_f32<32>(lo0 | (h0 << 4), q);
         bytes_to_f32<32>(lo1 | (h1 << 4), q + 4);
+#pragma unroll
+        for (int i = 0; i < 8; i++) y[i] = __fmul_rn(s.x, q[i]);
+    }
+    GGB_UNPACK_RUN
+};
+
+template <> struct Unpack8<T_IQ4_NL> {     // y = d * kvalues[q]                 gguf-py quants.py IQ4_NL; dequantize.cuh:400-416
+    static constexpr int NSUB = 1;
+    __device__ __forceinline__ static int sub_of(int) { return 0; }
+    __device__ __forceinline__ static float2 sub_scale(const uint8_t *b, int) { return make_float2(ggb_h2f(ld_u16(b)), 0.0f); }
+    __device__ __forceinline__ static void run_sc(const uint8_t *b, int p, float2 s, float (&y)[8]) {
+        const uint8_t *src = b + 2 + 8 * (p & 1);
+        const int sh = 4 * (p >> 1);
+        float q[8];
+        bytes_to_f32<128>(iq4nl_lut4((ld_u32_a2(src) >> sh) & 0x0f0f0f0fu) ^ 0x80808080u, q);
+        bytes_to_f32<128>(iq4nl_lut4((ld_u32_a2(src + 4) >> sh) & 0x0f0f0f0fu) ^ 0x80808080u, q + 4);
+#pragma unroll
+        for (int i = 0; i < 8; i++) y[i] = __fmul_rn(s.x, q[i]);
+    }
+    GGB_UNPACK_RUN
+};
+
+template <> struct Unpack8<T_IQ4_XS> {     // y = (d*(ls-32)) * kvalues[q]       gguf-py quants.py IQ4_XS; dequantize.cuh:419-433
+    static constexpr int NSUB = 8;
+    __device__ __forceinline__ static int sub_of(int p) { return p >> 2; }
+    __device__ __forceinline__ static float2 sub_scale(const uint8_t *b, int ib) {
+        return make_float2(__fmul_rn(ggb_h2f(ld_u16(b)), (float)iq4xs_scale(b, ib)), 0.0f);
+    }
+    __device__ __forceinline__ static void run_sc(const uint8_t *b, int p, float2 s, float (&y)[8]) {
+        const uint8_t *src = b + 8 + 16 * (p >> 2) + 8 * (p & 1);
+        const int sh = 4 * ((p >> 1) & 1);
+        float q[8];
+        bytes_to_f32<128>(iq4nl_lut4((ld_u32_a4(src) >> sh) & 0x0f0f0f0fu) ^ 0x80808080u, q);
+        bytes_to_f32<128>(iq4nl_lut4((ld_u32_a4(src + 4) >> sh) & 0x0f0f0f0fu) ^ 0x80808080u, q + 4);
 #pragma unroll
         for (int i = 0; i < 8; i++) y[i] = __fmul_rn(s.x, q[i]);
     }

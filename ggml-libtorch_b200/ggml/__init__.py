@@ -23,7 +23,7 @@ __all__ = [
     "ggml_dequantize", "ggml_mul_mat_vec_a8", "ggml_mul_mat_a8", "ggml_quantize_q8_1",
     "dequantize_out", "mul_mat_vec_a8_out", "mul_mat_a8_out", "mmq_workspace_bytes", "mmvq_workspace_bytes",
     "set_option", "GGB_OPT_STATIC_WEIGHTS", "mul_mat_vec_a8_gather", "mul_mat_vec_a8_fused",
-    "block_elems", "block_bytes", "SUPPORTED_TYPES", "MMVQ_MAX_BATCH",
+    "block_elems", "block_bytes", "SUPPORTED_TYPES", "MMQ_TYPES", "MMVQ_MAX_BATCH",
 ]
 
 _lib = _capi.lib
@@ -31,7 +31,8 @@ _DT = {torch.float32: GGB_F32, torch.float16: GGB_F16, torch.bfloat16: GGB_BF16}
 _DT_INV = {v: k for k, v in _DT.items()}
 
 # ggml_type ids, ggml/ggml-common.h:1128-1161
-SUPPORTED_TYPES = (2, 3, 6, 7, 8, 10, 11, 12, 13, 14)
+SUPPORTED_TYPES = (2, 3, 6, 7, 8, 10, 11, 12, 13, 14, 20, 23)
+MMQ_TYPES = (2, 3, 6, 7, 8, 10, 11, 12, 13, 14)      # IQ4_NL (20) / IQ4_XS (23): dequantize + MMVQ only, as in the reference
 MMVQ_MAX_BATCH = 8
 
 

@@ -10,11 +10,12 @@ from __future__ import annotations
 import numpy as np
 
 BLOCK = {2: (32, 18), 3: (32, 20), 6: (32, 22), 7: (32, 24), 8: (32, 34),
-         10: (256, 84), 11: (256, 110), 12: (256, 144), 13: (256, 176), 14: (256, 210)}
+         10: (256, 84), 11: (256, 110), 12: (256, 144), 13: (256, 176), 14: (256, 210),
+         20: (32, 18), 23: (256, 136)}
 HALF_OFFSETS = {2: [0], 3: [0, 2], 6: [0], 7: [0, 2], 8: [0],
-                10: [80, 82], 11: [108], 12: [0, 2], 13: [0, 2], 14: [208]}
+                10: [80, 82], 11: [108], 12: [0, 2], 13: [0, 2], 14: [208], 20: [0], 23: [0]}
 NAMES = {2: "Q4_0", 3: "Q4_1", 6: "Q5_0", 7: "Q5_1", 8: "Q8_0",
-         10: "Q2_K", 11: "Q3_K", 12: "Q4_K", 13: "Q5_K", 14: "Q6_K"}
+         10: "Q2_K", 11: "Q3_K", 12: "Q4_K", 13: "Q5_K", 14: "Q6_K", 20: "IQ4_NL", 23: "IQ4_XS"}
 
 
 def weight_bytes(qtype: int, rows: int, cols: int) -> int:

@@ -19,11 +19,15 @@ _REF_PATH = os.path.join(_HERE, "_ref", "custom_ops.so")
 
 Q4_0, Q4_1, Q5_0, Q5_1, Q8_0, Q8_1 = 2, 3, 6, 7, 8, 9
 Q2_K, Q3_K, Q4_K, Q5_K, Q6_K = 10, 11, 12, 13, 14
+IQ4_NL, IQ4_XS = 20, 23
 LEGACY_TYPES = (Q4_0, Q4_1, Q5_0, Q5_1, Q8_0)
 K_TYPES = (Q2_K, Q3_K, Q4_K, Q5_K, Q6_K)
-ALL_TYPES = LEGACY_TYPES + K_TYPES
+ALL_TYPES = LEGACY_TYPES + K_TYPES           # dequantize + MMVQ + MMQ
+IQ_TYPES = (IQ4_NL, IQ4_XS)                  # dequantize + MMVQ only (the reference has no MMQ for them either)
+VEC_TYPES = ALL_TYPES + IQ_TYPES
+BLOCK32_TYPES = LEGACY_TYPES + (IQ4_NL,)     # 32-value blocks: K only needs to be a multiple of 32
 TYPE_NAMES = {2: "Q4_0", 3: "Q4_1", 6: "Q5_0", 7: "Q5_1", 8: "Q8_0", 9: "Q8_1",
-              10: "Q2_K", 11: "Q3_K", 12: "Q4_K", 13: "Q5_K", 14: "Q6_K"}
+              10: "Q2_K", 11: "Q3_K", 12: "Q4_K", 13: "Q5_K", 14: "Q6_K", 20: "IQ4_NL", 23: "IQ4_XS"}
 
 
 def build(force: bool = False) -> str:
@@ -194,7 +198,8 @@ def random_weights(qtype: int, rows: int, cols: int, seed: int = 0) -> np.ndarra
     rng = np.random.default_rng(seed)
     blocks = rng.integers(0, 256, size=(nb, bs), dtype=np.uint8)
     half_offsets = {Q4_0: [0], Q4_1: [0, 2], Q5_0: [0], Q5_1: [0, 2], Q8_0: [0],
-                    Q2_K: [80, 82], Q3_K: [108], Q4_K: [0, 2], Q5_K: [0, 2], Q6_K: [208]}[qtype]
+                    Q2_K: [80, 82], Q3_K: [108], Q4_K: [0, 2], Q5_K: [0, 2], Q6_K: [208],
+                    IQ4_NL: [0], IQ4_XS: [0]}[qtype]
     for off in half_offsets:
         h = (rng.uniform(0.5, 1.5, size=nb) * 2.0 ** -10).astype(np.float16)
         blocks[:, off:off + 2] = h.view(np.uint8).reshape(nb, 2)

@@ -11,6 +11,10 @@
  *     block structs ggml/ggml-common.h:67-108, fp32 operation order of gguf-py 0.19.0
  *     gguf/quants.py:404-572 (third-party `gguf`, pinned >=0.10.0 by requirements-dev.txt:3;
  *     it is the expected-value source of every reference test)
+ *   - IQ4_NL / IQ4_XS dequantize: block structs ggml/ggml-common.h (block_iq4_nl,
+ *     block_iq4_xs), element layout ggml/dequantize.cuh:400-433, the 16-entry codebook kvalues_iq4nl
+ *     (ggml-common.h:1060), fp32 operation order of gguf-py quants.py (classes IQ4_NL, IQ4_XS); MMVQ math
+ *     ggml/vecdotq.cuh:842-888.  The reference has no MMQ for these two types and neither has orc_mmq.
  *   - q8_1 activation quantization               ggml/ggml_kernel.cu:13-50
  *   - q8_1_mmq activation quantization           ggml/mmq.cu:84-154, ggml/mmq.cuh:176-181
  *   - MMVQ math (integer dots + scale algebra)   ggml/vecdotq.cuh:45-345, 347-605; ggml/mmvq.cuh:2-38
@@ -104,6 +108,8 @@ int orc_block_elems(int type) {
     switch (type) {
         case ORC_Q4_0: case ORC_Q4_1: case ORC_Q5_0: case ORC_Q5_1: case ORC_Q8_0: case ORC_Q8_1: return 32;
         case ORC_Q2_K: case ORC_Q3_K: case ORC_Q4_K: case ORC_Q5_K: case ORC_Q6_K: return 256;
+        case ORC_IQ4_NL: return 32;
+        case ORC_IQ4_XS: return 256;
         default: return 0;
     }
 }
@@ -114,6 +120,7 @@ int orc_block_bytes(int type) {
         case ORC_Q5_1: return 24;  case ORC_Q8_0: return 34;  case ORC_Q8_1: return 36;
         case ORC_Q2_K: return 84;  case ORC_Q3_K: return 110; case ORC_Q4_K: return 144;
         case ORC_Q5_K: return 176; case ORC_Q6_K: return 210;
+        case ORC_IQ4_NL: return 18; case ORC_IQ4_XS: return 136;
         default: return 0;
     }
 }
@@ -140,6 +147,17 @@ static inline int q3k_scale(const uint8_t *s, int is) {
 
 /* Write the 32 or 256 integer quants of one block, in element order, before any scaling.
  * For types with an additive offset (q-8, q-16, q-32, q3 -4) the offset is already applied. */
+/* the non-linear 4-bit codebook of IQ4_NL / IQ4_XS (a format constant: ggml-common.h:1060, gguf-py IQ4_NL.kvalues) */
+static const int8_t kvalues_iq4nl[16] = {-127, -104, -83, -65, -49, -35, -22, -10, 1, 13, 25, 38, 53, 69, 89, 113};
+
+/* IQ4_XS 6-bit sub-block scale ib (0..7), offset -32 applied: low 4 bits from scales_l (bytes 4..7), high 2 from scales_h
+ * (bytes 2..3)   (dequantize.cuh:426-427, vecdotq.cuh:877) */
+static inline int iq4xs_scale(const uint8_t *b, int ib) {
+    const int lo = (b[4 + ib / 2] >> (4 * (ib % 2))) & 0x0f;
+    const int hi = (ld16(b + 2) >> (2 * ib)) & 3;
+    return (lo | (hi << 4)) - 32;
+}
+
 static void unpack_block_ints(int type, const uint8_t *b, int *q) {
     switch (type) {
     case ORC_Q4_0:                                   /* ggml-quants.hpp:11-20 */
@@ -198,6 +216,15 @@ static void unpack_block_ints(int type, const uint8_t *b, int *q) {
             q[128 * ip + 96 + l] = ((ql[l + 32] >> 4)   | (((h >> 6) & 3) << 4)) - 32;
         }
         break;
+    case ORC_IQ4_NL:                                 /* dequantize.cuh:400-416: codebook values */
+        for (int j = 0; j < 16; j++) { q[j] = kvalues_iq4nl[b[2 + j] & 0x0f]; q[j + 16] = kvalues_iq4nl[b[2 + j] >> 4]; }
+        break;
+    case ORC_IQ4_XS:                                 /* dequantize.cuh:419-433 */
+        for (int ib = 0; ib < 8; ib++) for (int j = 0; j < 16; j++) {
+            q[32 * ib + j]      = kvalues_iq4nl[b[8 + 16 * ib + j] & 0x0f];
+            q[32 * ib + 16 + j] = kvalues_iq4nl[b[8 + 16 * ib + j] >> 4];
+        }
+        break;
     default: break;
     }
 }
@@ -249,6 +276,17 @@ static void dequant_block(int type, const uint8_t *b, float *y) {
         for (int is = 0; is < 16; is++) {
             const float dl = d * (float)(int8_t)b[192 + is];
             for (int l = 0; l < 16; l++) y[16 * is + l] = dl * (float)q[16 * is + l];
+        }
+        break; }
+    case ORC_IQ4_NL: {                               /* gguf-py IQ4_NL: y = d * kvalues[q] */
+        const float d = h2f(ld16(b));
+        for (int j = 0; j < 32; j++) y[j] = d * (float)q[j];
+        break; }
+    case ORC_IQ4_XS: {                               /* gguf-py IQ4_XS: dl = d * (ls - 32); y = dl * kvalues[q] */
+        const float d = h2f(ld16(b));
+        for (int ib = 0; ib < 8; ib++) {
+            const float dl = d * (float)iq4xs_scale(b, ib);
+            for (int l = 0; l < 32; l++) y[32 * ib + l] = dl * (float)q[32 * ib + l];
         }
         break; }
     default: break;
@@ -507,6 +545,20 @@ static double row_dot(int type, const uint8_t *w, int64_t K, const int8_t *q8, c
             }
             acc += (double)d * sf;
             break; }
+        case ORC_IQ4_NL: {                           /* vecdotq.cuh:842-864 */
+            int sumi = 0;
+            for (int j = 0; j < 32; j++) sumi += q[j] * a[j];
+            const float d = h2f(ld16(b));
+            acc += (double)(d * dd[0]) * sumi;
+            break; }
+        case ORC_IQ4_XS: {                           /* vecdotq.cuh:867-888 */
+            const float d = h2f(ld16(b));
+            for (int ib = 0; ib < 8; ib++) {
+                int sumi = 0;
+                for (int l = 0; l < 32; l++) sumi += q[32 * ib + l] * a[32 * ib + l];
+                acc += (double)d * (double)iq4xs_scale(b, ib) * (double)dd[ib] * sumi;
+            }
+            break; }
         default: break;
         }
     }
@@ -542,7 +594,7 @@ int orc_mmvq(const void *W, int type, const void *q8_1, int64_t B, int64_t K, in
  * -> Y[M][N] fp32, dst[j*N+i] as mmq.cuh:1764-1790. */
 int orc_mmq(const void *W, int type, const void *q8_1_mmq, int64_t M, int64_t K, int64_t N, float *Y) {
     const int qk = orc_block_elems(type), bs = orc_block_bytes(type);
-    if (qk == 0 || type == ORC_Q8_1) return -1;
+    if (qk == 0 || type == ORC_Q8_1 || type == ORC_IQ4_NL || type == ORC_IQ4_XS) return -1;   /* mmq.cu:222-252: no IQ case */
     if (K % qk) return -2;
     const int need_sum = orc_mmq_need_sum(type);
     const int64_t Kp = K - K % 512 + 512, ng = Kp / 32;

@@ -7,7 +7,7 @@ Sources of truth (nothing from oracle/ggml_oracle.c is used here):
     /root/reference/ggml-cpu/custom_ops.cpp (oracle/build_ref.py) for the five legacy types.
 
 Weights: `gguf.quants.quantize(randn * 0.02)` for the legacy types (the reference fixtures are made
-that way) and random valid block bytes for the K-quants (gguf-py cannot quantize them), plus
+that way) and random valid block bytes for the K-quants and IQ4_NL / IQ4_XS (gguf-py cannot quantize them), plus
 hand-built edge-case blocks.  Run:  python tests/golden/make_golden.py
 """
 import os
@@ -29,7 +29,8 @@ OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "dequant_golden.n
 def edge_blocks(t):
     """A few adversarial blocks: zero / max payloads, d = 0, negative, subnormal and max-normal fp16 scales."""
     qk, bs = oracle.block_elems(t), oracle.block_bytes(t)
-    offs = {2: [0], 3: [0, 2], 6: [0], 7: [0, 2], 8: [0], 10: [80, 82], 11: [108], 12: [0, 2], 13: [0, 2], 14: [208]}[t]
+    offs = {2: [0], 3: [0, 2], 6: [0], 7: [0, 2], 8: [0], 10: [80, 82], 11: [108], 12: [0, 2], 13: [0, 2], 14: [208],
+            20: [0], 23: [0]}[t]
     halves = np.array([0.0, -0.0, 1.0, -1.0, 6.0e-8, -6.0e-8, 65504.0, 0.333251953125, 1e-3, -2.5], dtype=np.float16)
     rng = np.random.default_rng(1234 + t)
     blocks = []
@@ -55,7 +56,7 @@ def main():
     assert ref is not None, "the reference CPU op must be built (oracle/build_ref.py) to make golden vectors"
     data = {}
     rng = np.random.default_rng(0)
-    for t in oracle.ALL_TYPES:
+    for t in oracle.VEC_TYPES:
         name = oracle.TYPE_NAMES[t]
         rows, cols = 6, 512
         if t in oracle.LEGACY_TYPES:

@@ -36,7 +36,8 @@ def test_version_and_geometry(capi):
     L = capi.lib
     assert L.ggb_version() == 100
     want = {2: (32, 18), 3: (32, 20), 6: (32, 22), 7: (32, 24), 8: (32, 34),
-            10: (256, 84), 11: (256, 110), 12: (256, 144), 13: (256, 176), 14: (256, 210)}
+            10: (256, 84), 11: (256, 110), 12: (256, 144), 13: (256, 176), 14: (256, 210),
+            20: (32, 18), 23: (256, 136)}
     for t, (qk, bs) in want.items():
         assert L.ggb_block_elems(t) == qk and L.ggb_block_bytes(t) == bs
     for t in (0, 1, 9, 15, 16, 99, -1):

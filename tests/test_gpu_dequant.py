@@ -13,7 +13,7 @@ from util import DEQUANT_ATOL, DEQUANT_RTOL, GOLDEN, assert_bits_equal, bf16_bit
 
 pytestmark = pytest.mark.gpu
 
-TYPES = oracle.ALL_TYPES
+TYPES = oracle.VEC_TYPES
 IDS = [oracle.TYPE_NAMES[t] for t in TYPES]
 DTYPES = [torch.float32, torch.float16, torch.bfloat16]
 
@@ -68,7 +68,7 @@ def test_random_shapes(ops, t, shape, dtype):
     _check(ops, w, t, m, n, dtype, f"{oracle.TYPE_NAMES[t]} {shape}")
 
 
-@pytest.mark.parametrize("t", oracle.LEGACY_TYPES, ids=[oracle.TYPE_NAMES[t] for t in oracle.LEGACY_TYPES])
+@pytest.mark.parametrize("t", oracle.BLOCK32_TYPES, ids=[oracle.TYPE_NAMES[t] for t in oracle.BLOCK32_TYPES])
 def test_legacy_block_granularity(ops, t):
     """legacy types only need n % 32 == 0: rows that are not a multiple of the 8192-value tile."""
     for m, n in [(1, 32), (7, 96), (129, 160)]:
@@ -93,7 +93,7 @@ def test_empty_and_errors(ops):
     with pytest.raises(ValueError):
         ops.ggml_dequantize(w, 12, 1, 512)          # wrong byte count
     with pytest.raises(ValueError):
-        ops.ggml_dequantize(w, 16, 1, 256)          # IQ type: out of scope
+        ops.ggml_dequantize(w, 16, 1, 256)          # IQ2_XXS: codebook IQ types are not built (remainder)
     with pytest.raises(ValueError):
         ops.ggml_dequantize(w.view(torch.int8), 12, 1, 256)
 
@@ -107,7 +107,7 @@ def test_config1_full_size(ops, t):
     _check(ops, w, t, 4096, 4096, torch.float32, "config1")
 
 
-@pytest.mark.parametrize("t", oracle.K_TYPES, ids=[oracle.TYPE_NAMES[t] for t in oracle.K_TYPES])
+@pytest.mark.parametrize("t", oracle.K_TYPES + (oracle.IQ4_XS,), ids=[oracle.TYPE_NAMES[t] for t in oracle.K_TYPES + (oracle.IQ4_XS,)])
 def test_config2_full_size(ops, t):
     """BASELINE config 2: 4096x14336 K-quants to fp16/bf16, bit-exact vs the (threaded) oracle."""
     m, n = 4096, 14336

@@ -143,3 +143,12 @@ def test_errors(ops):
         ops.ggml_mul_mat_a8(w, torch.zeros(3, 512, device="cuda"), 12, 4)
     with pytest.raises(ValueError):
         ops.ggml_mul_mat_a8(w, torch.zeros(256, device="cuda"), 12, 4)
+
+
+@pytest.mark.parametrize("t", oracle.IQ_TYPES, ids=[oracle.TYPE_NAMES[t] for t in oracle.IQ_TYPES])
+def test_iq4_has_no_mmq(ops, t):
+    """IQ4_NL / IQ4_XS: dequantize + MMVQ only.  The reference's ggml_mul_mat_a8 has no case for them either and
+    returns uninitialised memory (mmq.cu:222-252); here the call fails loudly."""
+    w = torch.from_numpy(oracle.random_weights(t, 4, 512, seed=0)).cuda()
+    with pytest.raises(ValueError):
+        ops.ggml_mul_mat_a8(w, torch.zeros(16, 512, device="cuda"), t, 4)

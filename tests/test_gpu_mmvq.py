@@ -15,7 +15,7 @@ from util import MMVQ_ATOL, MMVQ_RTOL
 
 pytestmark = pytest.mark.gpu
 
-TYPES = oracle.ALL_TYPES
+TYPES = oracle.VEC_TYPES
 IDS = [oracle.TYPE_NAMES[t] for t in TYPES]
 DTYPES = [torch.float32, torch.float16, torch.bfloat16]
 OUT_REL = {torch.float32: 0.0, torch.float16: 2.0 ** -10, torch.bfloat16: 2.0 ** -7}
@@ -58,7 +58,7 @@ def test_shapes(ops, t, shape, dtype):
     _check(ops, t, N, K, 3, dtype, seed=N + 1)
 
 
-@pytest.mark.parametrize("t", oracle.LEGACY_TYPES, ids=[oracle.TYPE_NAMES[t] for t in oracle.LEGACY_TYPES])
+@pytest.mark.parametrize("t", oracle.BLOCK32_TYPES, ids=[oracle.TYPE_NAMES[t] for t in oracle.BLOCK32_TYPES])
 def test_legacy_k_multiple_of_32(ops, t):
     """legacy types only need K % 32 == 0 (rows then are not 16-byte aligned: the non-TMA path)."""
     for N, K in [(17, 32), (40, 96), (9, 2080)]:
