@@ -82,6 +82,25 @@ __device__ __forceinline__ uint32_t iq4nl_lut4(uint32_t w) {
     const uint32_t m = ((w >> 3) & 0x01010101u) * 0xffu;
     return (hi & m) | (lo & ~m);
 }
+// The same lookup for all eight codes of a raw qs word at once (MMVQ fast path): the 3-bit nibbles of q & 0x77777777 ARE
+// PRMT selectors, so four PRMTs look bytes [l0 h0 l1 h1] / [l2 h2 l3 h3] up in both table halves, four more split them into
+// low-nibble and high-nibble words, and bit 3 of every code picks the half through a sign-replicating PRMT (selector
+// nibbles 8..B; inline PTX because __byte_perm only honours three selector bits).  15 instructions per 8 values.
+__device__ __forceinline__ uint32_t ggb_prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+__device__ __forceinline__ void iq4nl_lut8(uint32_t q, uint32_t &vlo, uint32_t &vhi) {
+    const uint32_t s = q & 0x77777777u, s2 = s >> 16;
+    const uint32_t al = ggb_prmt(0xBFAD9881u, 0xF6EADDCFu, s), bl = ggb_prmt(0xBFAD9881u, 0xF6EADDCFu, s2);
+    const uint32_t ah = ggb_prmt(0x26190D01u, 0x71594535u, s), bh = ggb_prmt(0x26190D01u, 0x71594535u, s2);
+    const uint32_t mlo = ggb_prmt(q << 4, 0u, 0xBA98u), mhi = ggb_prmt(q, 0u, 0xBA98u);
+    const uint32_t lo_l = ggb_prmt(al, bl, 0x6420u), lo_h = ggb_prmt(ah, bh, 0x6420u);
+    const uint32_t hi_l = ggb_prmt(al, bl, 0x7531u), hi_h = ggb_prmt(ah, bh, 0x7531u);
+    vlo = (lo_h & mlo) | (lo_l & ~mlo);
+    vhi = (hi_h & mhi) | (hi_l & ~mhi);
+}
 // IQ4_XS 6-bit sub-block scale ib (0..7) with the -32 offset applied (dequantize.cuh:426-427)
 __device__ __forceinline__ int iq4xs_scale(const uint8_t *b, int ib) {
     const int lo = (b[4 + (ib >> 1)] >> (4 * (ib & 1))) & 0x0f;

@@ -90,6 +90,21 @@ __device__ __forceinline__ int q3k_scale(const uint8_t *s, int is) {
     return (lo | (hi << 4)) - 32;
 }
 
+// NWORDS consecutive 32-bit words from a 2-byte-aligned shared address: NWORDS + 1 aligned loads and funnel shifts
+// instead of 2 * NWORDS 16-bit loads (the 16-bit loads of the 18/22/34-byte blocks kept the LSU queue full: 45 % of all
+// stall samples of the Q8_0 kernel were on them).  May read up to 4 bytes past the last word: still inside the stage ring.
+template <int NWORDS>
+__device__ __forceinline__ void lds_words_a2(const uint8_t *a, uint32_t (&out)[NWORDS]) {
+    const uintptr_t u = reinterpret_cast<uintptr_t>(a);
+    const uint32_t *p = reinterpret_cast<const uint32_t *>(u & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(u & 2) * 8;
+    uint32_t w[NWORDS + 1];
+#pragma unroll
+    for (int i = 0; i <= NWORDS; i++) w[i] = p[i];
+#pragma unroll
+    for (int i = 0; i < NWORDS; i++) out[i] = __funnelshift_r(w[i], w[i + 1], sh);
+}
+
 // Unpack group `g` (32 values) of a staged row segment that starts on a block boundary.
 template <int TYPE>
 __device__ __forceinline__ void load_group(const uint8_t *seg, int g, GroupW &o) {
@@ -98,11 +113,12 @@ __device__ __forceinline__ void load_group(const uint8_t *seg, int g, GroupW &o)
     if constexpr (TYPE == T_Q4_0) {
         const uint8_t *b = seg + g * BS;
         o.a0 = o.a1 = ggb_h2f(ld_u16(b));
+        uint32_t qs[4];
+        lds_words_a2<4>(b + 2, qs);
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            const uint32_t q = ld_u32_a2(b + 2 + 4 * i);
-            o.w[i] = q & 0x0f0f0f0fu;
-            o.w[4 + i] = (q >> 4) & 0x0f0f0f0fu;
+            o.w[i] = qs[i] & 0x0f0f0f0fu;
+            o.w[4 + i] = (qs[i] >> 4) & 0x0f0f0f0fu;
         }
     } else if constexpr (TYPE == T_Q4_1) {
         const uint8_t *b = seg + g * BS;
@@ -117,10 +133,12 @@ __device__ __forceinline__ void load_group(const uint8_t *seg, int g, GroupW &o)
     } else if constexpr (TYPE == T_Q5_0) {
         const uint8_t *b = seg + g * BS;
         o.a0 = o.a1 = ggb_h2f(ld_u16(b));
-        const uint32_t qh = ld_u32_a2(b + 2);
+        uint32_t hq[5];                                      // qh, then the 16 bytes of nibbles
+        lds_words_a2<5>(b + 2, hq);
+        const uint32_t qh = hq[0];
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            const uint32_t q = ld_u32_a2(b + 6 + 4 * i);
+            const uint32_t q = hq[1 + i];
             o.w[i] = (q & 0x0f0f0f0fu) | spread4((qh >> (4 * i)) & 0xf);
             o.w[4 + i] = ((q >> 4) & 0x0f0f0f0fu) | spread4((qh >> (16 + 4 * i)) & 0xf);
         }
@@ -138,8 +156,7 @@ __device__ __forceinline__ void load_group(const uint8_t *seg, int g, GroupW &o)
     } else if constexpr (TYPE == T_Q8_0) {
         const uint8_t *b = seg + g * BS;
         o.a0 = o.a1 = ggb_h2f(ld_u16(b));
-#pragma unroll
-        for (int i = 0; i < 8; i++) o.w[i] = ld_u32_a2(b + 2 + 4 * i);
+        lds_words_a2<8>(b + 2, o.w);
     } else if constexpr (TYPE == T_Q2_K) {
         const uint8_t *b = seg + (g >> 3) * BS;
         const int j = g & 7, n = j >> 2, s = j & 3;
@@ -188,21 +205,17 @@ __device__ __forceinline__ void load_group(const uint8_t *seg, int g, GroupW &o)
     } else if constexpr (TYPE == T_IQ4_NL) {
         const uint8_t *b = seg + g * BS;
         o.a0 = o.a1 = ggb_h2f(ld_u16(b));
+        uint32_t qs[4];
+        lds_words_a2<4>(b + 2, qs);
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const uint32_t q = ld_u32_a2(b + 2 + 4 * i);
-            o.w[i] = iq4nl_lut4(q & 0x0f0f0f0fu);            // codebook values as int8 bytes
-            o.w[4 + i] = iq4nl_lut4((q >> 4) & 0x0f0f0f0fu);
-        }
+        for (int i = 0; i < 4; i++) iq4nl_lut8(qs[i], o.w[i], o.w[4 + i]);      // codebook values as int8 bytes
     } else if constexpr (TYPE == T_IQ4_XS) {
         const uint8_t *b = seg + (g >> 3) * BS;
         const int ib = g & 7;
         o.a0 = o.a1 = ggb_h2f(ld_u16(b)) * (float)iq4xs_scale(b, ib);
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            const uint32_t q = ld_u32_a4(b + 8 + 16 * ib + 4 * i);
-            o.w[i] = iq4nl_lut4(q & 0x0f0f0f0fu);
-            o.w[4 + i] = iq4nl_lut4((q >> 4) & 0x0f0f0f0fu);
+            iq4nl_lut8(ld_u32_a4(b + 8 + 16 * ib + 4 * i), o.w[i], o.w[4 + i]);
         }
     } else {   // T_Q6_K
         const uint8_t *b = seg + (g >> 3) * BS;

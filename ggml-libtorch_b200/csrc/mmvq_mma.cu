@@ -272,6 +272,61 @@ template <> struct MmaOps<T_Q5_K> {
     }
 };
 
+// ---- IQ4_XS: d @0, scales_h @2 (2 bits x 8), scales_l @4 (4 bits x 8), 128 bytes of 4-bit codebook indices @8; 136-byte
+// blocks are 8-byte aligned.  Value = d * (ls - 32) * kvalues_iq4nl[code] (dequantize.cuh:419-433, vecdotq.cuh:867-888).
+// The codebook values ARE int8, so after the register lookup (iq4nl_lut8: eight codes per raw word) they go straight into
+// the s8 MMA: lane t owns bytes 4t..4t+3 of the sub-block's 16 code bytes = values 4t..4t+3 (low nibbles, a0/a1) and
+// 16+4t..16+4t+3 (high nibbles, a2/a3), and reads the matching activation bytes for B.  No minima, no offset.
+template <> struct MmaOps<T_IQ4_XS> {
+    static constexpr int BS = 136;
+    static constexpr bool S16 = false;
+    __device__ __forceinline__ static float scale_of(uint2 hd, int ib) {
+        const int ls = (int)(((hd.y >> (4 * ib)) & 0xfu) | (((hd.x >> (16 + 2 * ib)) & 3u) << 4)) - 32;
+        return __int_as_float(ls + kMagicBits) - kMagic;     // exact
+    }
+    __device__ __forceinline__ static void step(const uint8_t *r0, const uint8_t *r1, const uint8_t *ap, const float2 *dp,
+                                                const float2 *, int *scr, int q, int t, float (&acc)[4]) {
+        const uint2 h0 = lds64(r0), h1 = lds64(r1);
+        // lane t decodes sub-blocks t, t + 4 of rows q, q + 8 into the warp's scratch (row-major, {s[t], s[t+4]} by t)
+        float *fscr = reinterpret_cast<float *>(scr);
+        *reinterpret_cast<float2 *>(fscr + q * 8 + 2 * t) = make_float2(scale_of(h0, t), scale_of(h0, t + 4));
+        *reinterpret_cast<float2 *>(fscr + (q + 8) * 8 + 2 * t) = make_float2(scale_of(h1, t), scale_of(h1, t + 4));
+        __syncwarp();
+        float s0[8], s1[8];                                      // s0[2j] = sub-block j, s0[2j+1] = sub-block j + 4 (row q); s1: row q + 8
+        {
+            const float4 a = *reinterpret_cast<const float4 *>(fscr + q * 8), b = *reinterpret_cast<const float4 *>(fscr + q * 8 + 4);
+            const float4 c = *reinterpret_cast<const float4 *>(fscr + (q + 8) * 8), d = *reinterpret_cast<const float4 *>(fscr + (q + 8) * 8 + 4);
+            s0[0] = a.x; s0[1] = a.y; s0[2] = a.z; s0[3] = a.w; s0[4] = b.x; s0[5] = b.y; s0[6] = b.z; s0[7] = b.w;
+            s1[0] = c.x; s1[1] = c.y; s1[2] = c.z; s1[3] = c.w; s1[4] = d.x; s1[5] = d.y; s1[6] = d.z; s1[7] = d.w;
+        }
+        float fs[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int ib = 0; ib < 8; ib++) {
+            const uint32_t w0 = *reinterpret_cast<const uint32_t *>(r0 + 8 + 16 * ib + 4 * t);
+            const uint32_t w1 = *reinterpret_cast<const uint32_t *>(r1 + 8 + 16 * ib + 4 * t);
+            const uint32_t b0 = *reinterpret_cast<const uint32_t *>(ap + 32 * ib + 4 * t);
+            const uint32_t b1 = *reinterpret_cast<const uint32_t *>(ap + 32 * ib + 16 + 4 * t);
+            uint32_t a0, a1, a2, a3;
+            iq4nl_lut8(w0, a0, a2);
+            iq4nl_lut8(w1, a1, a3);
+            int c[4];
+            mma_s8(c, a0, a1, a2, a3, b0, b1);
+            const float2 d8 = dp[ib];
+            const int si = 2 * (ib & 3) + (ib >> 2);
+            // |dot| <= 32 * 127 * 127 < 2^22: exact int -> float through the mantissa of 1.5 * 2^23
+            fs[0] = fmaf(__int_as_float(c[0] + kMagicBits) - kMagic, d8.x * s0[si], fs[0]);
+            fs[1] = fmaf(__int_as_float(c[1] + kMagicBits) - kMagic, d8.y * s0[si], fs[1]);
+            fs[2] = fmaf(__int_as_float(c[2] + kMagicBits) - kMagic, d8.x * s1[si], fs[2]);
+            fs[3] = fmaf(__int_as_float(c[3] + kMagicBits) - kMagic, d8.y * s1[si], fs[3]);
+        }
+        const float d0 = ggb_h2f(h0.x & 0xffffu), d1 = ggb_h2f(h1.x & 0xffffu);
+        acc[0] += d0 * fs[0];
+        acc[1] += d0 * fs[1];
+        acc[2] += d1 * fs[2];
+        acc[3] += d1 * fs[3];
+    }
+};
+
 // ---- Q6_K: ql[128] @0, qh[64] @128, 16 int8 scales @192 (one per 16 values), d @208; 210-byte blocks are only
 // 2-byte aligned.  Value = d * sc * (q6 - 32): the weights go to the MMA as the unsigned q6 (one m16n8k16 per 16-value
 // sub-block), and the -32 becomes  - d * sum_sub sc[row, sub] * (32 * d8 * sum q8)[token, sub]: a 16 x 8 x 16 GEMM per
@@ -699,7 +754,7 @@ bool mma_applies(int type, int64_t B, int64_t K) {
     // measured crossover with the dp4a kernel (Llama-8B shapes): batch 3 for K = 4096, batch 2 for the long rows, where
     // the dp4a kernel's per-CTA activation quantization (3.3 us at K = 14336) costs more than the image kernel's launch
     const int64_t min_b = (g_min_batch == 3 && K > 8192) ? 2 : g_min_batch;
-    return (type == T_Q4_K || type == T_Q5_K || type == T_Q6_K) && B >= min_b && B <= 8 && K % 256 == 0 && K <= (1 << 16);
+    return (type == T_Q4_K || type == T_Q5_K || type == T_Q6_K || type == T_IQ4_XS) && B >= min_b && B <= 8 && K % 256 == 0 && K <= (1 << 16);
 }
 
 }  // namespace
@@ -726,6 +781,7 @@ int ggb_mmvq_mma_impl(const void *W, const void *X, void *Y, int type, int xy_dt
         case T_Q4_K: rc = dispatch_dtype<T_Q4_K>(W, X, Y, xy_dtype, B, K, N, ws, stream); break;
         case T_Q5_K: rc = dispatch_dtype<T_Q5_K>(W, X, Y, xy_dtype, B, K, N, ws, stream); break;
         case T_Q6_K: rc = dispatch_dtype<T_Q6_K>(W, X, Y, xy_dtype, B, K, N, ws, stream); break;
+        case T_IQ4_XS: rc = dispatch_dtype<T_IQ4_XS>(W, X, Y, xy_dtype, B, K, N, ws, stream); break;
         default: return 1;
     }
     if (rc != 1 || B < 6 || ggb_current_yout() || ggb_current_xin()) return rc;
