@@ -213,6 +213,52 @@ def config0_section(ggml, synth, dev, peaks, peak_kind):
     return out, launches
 
 
+def all_types_section(ggml, synth, dev, peaks, peak_kind):
+    """Every type the library serves, on one shape each: dequantize 4096x14336 -> fp16 (algorithmic bytes = blocks read +
+    fp16 written) and MMVQ 14336x4096 at batch 1 and 8 (weight bytes / time).  The headline sweep and the MMVQ section
+    above cover the K-quants of BASELINE's configs; this table shows where the legacy and IQ4 types stand."""
+    hbm = float(peaks["hbm_gbs"])
+    out = {"unit": "GB/s", "peak": hbm, "peak_source": peak_kind,
+           "method": "CUDA-graph replay over distinct weight copies (> 2x L2), median of 5 replays, fp16", "cases": []}
+    launches = 0
+    for t in ggml.SUPPORTED_TYPES:
+        case = {"type": synth.NAMES[t]}
+        # dequantize: 4 weight / output pairs per replay (4 x 117 MB of output > L2)
+        ws = [torch.from_numpy(synth.random_blocks(t, 4096, 14336, seed=i)).to(dev) for i in range(4)]
+        outs = [torch.empty((4096, 14336), dtype=torch.float16, device=dev) for _ in range(4)]
+
+        def run_dq():
+            for w, o in zip(ws, outs):
+                ggml.dequantize_out(w, t, 4096, 14336, o)
+
+        ms = _time_graph(run_dq, iters=5) / 4
+        launches += 4 * 9
+        nbytes = ws[0].numel() + 4096 * 14336 * 2
+        case["dequant_us"] = ms * 1e3
+        case["dequant_GBps"] = nbytes / (ms * 1e-3) / 1e9
+        del ws, outs
+        # MMVQ: 8 copies of the 14336 x 4096 matrix
+        N, K = 14336, 4096
+        base = torch.from_numpy(synth.random_blocks(t, N, K, seed=t)).to(dev)
+        copies = [base] + [base.clone() for _ in range(7)]
+        for B in (1, 8):
+            x = torch.randn(B, K, dtype=torch.float16, device=dev)
+            y = torch.empty(B, N, dtype=torch.float16, device=dev)
+            wsb = torch.empty(max(ggml.mmvq_workspace_bytes(t, B, K, N), 16), dtype=torch.uint8, device=dev)
+
+            def run_mv():
+                for w in copies:
+                    ggml.mul_mat_vec_a8_out(w, x, t, N, y, wsb)
+
+            ms = _time_graph(run_mv, iters=5) / 8
+            launches += 8 * 9
+            case[f"mmvq_b{B}_us"] = ms * 1e3
+            case[f"mmvq_b{B}_weight_GBps"] = base.numel() / (ms * 1e-3) / 1e9
+        del copies, base
+        out["cases"].append(case)
+    return out, launches
+
+
 def run(ggml, synth, dev, rank, world, peaks, peak_kind):
     extras = {}
     n = 0
@@ -229,7 +275,8 @@ def run(ggml, synth, dev, rank, world, peaks, peak_kind):
         if rank == 0:
             extras["tp_mlp"] = {"error": f"{type(e).__name__}: {e}"}
     if rank == 0:
-        for name, fn in (("config0_gpu", config0_section), ("mmvq", mmvq_section), ("mmq", mmq_section)):
+        for name, fn in (("config0_gpu", config0_section), ("mmvq", mmvq_section), ("mmq", mmq_section),
+                         ("all_types", all_types_section)):
             try:
                 extras[name], k = fn(ggml, synth, dev, peaks, peak_kind)
                 n += k

@@ -20,6 +20,7 @@ int64_t ggb_mmq_workspace_bytes_impl(int type, int64_t M, int64_t K, int64_t N);
 void ggb_mmvq_sb_set_static_weights(int on);
 void ggb_mmvq_sb_tune(int warps, int smem_cap_kb);
 void ggb_mmq_tune(int nb);
+void ggb_mmvq_tune_tiled(int max_box_bytes);
 void ggb_mmvq_sb_set_l2_prefetch(int mb);
 void ggb_mmvq_mma_tune(int cs, int s_log2_plus1, int min_batch);
 int ggb_mmvq_mma_impl(const void *W, const void *X, void *Y, int type, int xy_dtype, int64_t B, int64_t K, int64_t N,
@@ -112,6 +113,9 @@ int ggb_set_option(int option, int value) {
             return GGB_OK;
         case GGB_OPT_MMVQ_L2_PREFETCH:
             ggb_mmvq_sb_set_l2_prefetch(value);
+            return GGB_OK;
+        case GGB_OPT_MMVQ_TILED:
+            ggb_mmvq_tune_tiled(value);
             return GGB_OK;
         case GGB_OPT_MMVQ_MMA:
             ggb_mmvq_mma_tune(value & 0xff, (value >> 8) & 0xff, (value >> 16) & 0xff);

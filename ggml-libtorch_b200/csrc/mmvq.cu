@@ -20,6 +20,7 @@
 // (tests/test_gpu_mmvq.py): integer dots are exact; only the fp32 summation order differs from the
 // reference, so results agree with the oracle to ~1e-6 relative of the output scale.
 #include "q8_1.cuh"
+#include "tma2d.cuh"
 
 namespace {
 
@@ -43,6 +44,9 @@ struct Params {
     int seg_stride;      // shared-memory bytes per staged row segment (multiple of 16)
     int nstages;
     int fast;            // rows and segments are 16-byte aligned: TMA bulk copies
+    int nbox;            // > 0: a stage arrives as nbox 2-D tiled TMA boxes of (32 rows x box_bytes), one instruction each
+    int box_bytes;       //      (a bulk copy per row costs ~35 serialised instructions: UBLKCP takes uniform operands);
+    int gpb;             //      a box holds gpb = 64 / nbox whole 32-value groups of every row: [box][row][box_bytes]
     int x_vec;           // X is 16-byte aligned
     int off_scales;      // byte offsets into dynamic shared memory
     int off_stages;
@@ -267,7 +271,7 @@ __device__ __forceinline__ float combine(const GroupW &g, int dot0, int dot1, fl
 // ---------------------------------------------------------------- the kernel
 template <int TYPE, int B, typename T>
 __global__ void __launch_bounds__(kThreads, 1)
-mmvq_kernel(const Params p) {
+mmvq_kernel(const Params p, const __grid_constant__ CUtensorMap tmapW) {
     extern __shared__ __align__(128) uint8_t smem[];
     int8_t *act_q = reinterpret_cast<int8_t *>(smem);                          // [B][K]
     float2 *act_s = reinterpret_cast<float2 *>(smem + p.off_scales);           // [B][K/32] {d8, aux}
@@ -308,7 +312,14 @@ mmvq_kernel(const Params p) {
                 const int seg_bytes = min(p.chunk_bytes, p.row_bytes - c * p.chunk_bytes);
                 uint8_t *dst = stages + s * stage_bytes;
                 const uint8_t *src = wrow + (int64_t)c * p.chunk_bytes;
-                if (p.fast) {
+                if (p.nbox) {
+                    // rows past N and bytes past the row end are zero-filled and still counted: the stage is always whole
+                    if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
+                    __syncwarp();
+                    if (lane < p.nbox)
+                        tma_load_2d_hint(dst + lane * (kStageRows * p.box_bytes), &tmapW, (c * p.chunk_bytes + lane * p.box_bytes) >> 2,
+                                         (int)(r_begin + (int64_t)rg * kStageRows), &full[s], pol);
+                } else if (p.fast) {
                     if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)(nvalid * seg_bytes));
                     __syncwarp();
                     if (lane < nvalid)
@@ -379,13 +390,21 @@ mmvq_kernel(const Params p) {
             const int s = it % p.nstages;
             const uint32_t ph = (uint32_t)(it / p.nstages) & 1u;
             mbar_wait(&full[s], ph);
-            const uint8_t *seg0 = stages + s * stage_bytes + (warp * kRowsPerWarp) * p.seg_stride;
-            const uint8_t *seg1 = seg0 + p.seg_stride;
+            // row pitch inside the stage: the chunk's bytes, or one box's bytes in the tiled layout
+            const int pitch = p.nbox ? p.box_bytes : p.seg_stride;
+            const uint8_t *seg0 = stages + s * stage_bytes + (warp * kRowsPerWarp) * pitch;
             const int ng = min(kChunkGroups, ngroups_row - c * kChunkGroups);
             for (int g = lane; g < ng; g += 32) {
                 GroupW w0, w1;
-                load_group<TYPE>(seg0, g, w0);
-                load_group<TYPE>(seg1, g, w1);
+                int gl = g;
+                const uint8_t *sg = seg0;
+                if (p.nbox) {
+                    const int bx = g / p.gpb;
+                    gl = g - bx * p.gpb;
+                    sg = seg0 + bx * (kStageRows * p.box_bytes);
+                }
+                load_group<TYPE>(sg, gl, w0);
+                load_group<TYPE>(sg + pitch, gl, w1);
                 const int gk = c * kChunkGroups + g;
 #pragma unroll
                 for (int b = 0; b < B; b++) {
@@ -425,6 +444,15 @@ mmvq_kernel(const Params p) {
 }
 
 // ---------------------------------------------------------------- host side
+int g_max_box = -1;          // GGB_OPT_MMVQ_TILED: largest TMA box (bytes) of the tiled stages; 0 = per-row bulk copies; -1 = per type
+
+// Measured on one box (14336 x 4096 / 28672 x 8192, batch 1, tiled vs per-row copies): Q4_0 -6 / -17 %, Q4_1 -8 / -24 %,
+// Q2_K -9 / -18 % (the producer warp's ~1100 serialised instructions per stage were the bound); Q5_0 +3 / -4 %, Q3_K and
+// IQ4_NL +4 % (consumer-bound: nothing to gain, and a 32-row box is fetched row after row), Q8_0 +27 / +19 % (four boxes
+// of 544-byte runs); Q5_1 -2 / -12 %.  At batch 8 the consumers are the bound and tiled costs 3 %.  So: tiled where it
+// won (batch 1-2), per-row bulk copies elsewhere.
+template <int TYPE> constexpr bool kTiledByDefault = (TYPE == T_Q4_0 || TYPE == T_Q4_1 || TYPE == T_Q5_1 || TYPE == T_Q2_K);
+
 template <int TYPE, int B, typename T>
 int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, cudaStream_t stream) {
     constexpr int QK = BlockTraits<TYPE>::QK, BS = BlockTraits<TYPE>::BS;
@@ -441,6 +469,28 @@ int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, cudaStre
     const int seg = (int)(K < kChunkElems ? p.row_bytes : p.chunk_bytes);
     p.seg_stride = (seg + 15) & ~15;
     p.fast = ((reinterpret_cast<uintptr_t>(W) & 15) == 0) && (p.row_bytes % 16 == 0);
+    // tiled stage: split the chunk into nbox equal boxes of whole groups (super-blocks for the 256-value types), each a
+    // multiple of 16 bytes and at most 1024 (the TMA box limit of 256 uint32 elements); rows shorter than a chunk and
+    // block sizes that do not split that way (Q6_K: 210 bytes) keep the per-row bulk copies
+    p.nbox = p.box_bytes = p.gpb = 0;
+    const int max_box = g_max_box >= 0 ? g_max_box : ((kTiledByDefault<TYPE> && B <= 2) ? 1024 : 0);
+    if (p.fast && K >= kChunkElems && N <= 0x7fffffff) {
+        for (int nb = 1; nb <= 8; nb *= 2) {
+            const int bb = p.chunk_bytes / nb, gpb = kChunkGroups / nb;
+            if (bb <= max_box && bb % 16 == 0 && (gpb * 32) % QK == 0 && bb == gpb * 32 / QK * BS) {
+                p.nbox = nb;
+                p.box_bytes = bb;
+                p.gpb = gpb;
+                break;
+            }
+        }
+    }
+    alignas(64) CUtensorMap tmap;
+    memset(&tmap, 0, sizeof tmap);
+    if (p.nbox) {
+        const int rc = ggb_make_row_tensor_map(&tmap, W, N, p.row_bytes, kStageRows, p.box_bytes, "ggb_mmvq");
+        if (rc != GGB_OK) return rc;
+    }
     p.x_vec = (reinterpret_cast<uintptr_t>(X) & 15) == 0;
     const int act_q = (int)(B * K);
     p.off_scales = (act_q + 15) & ~15;
@@ -462,7 +512,7 @@ int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, cudaStre
         attr_set[di.dev] = true;
     }
     const int grid = (int)(N < di.sm_count ? N : di.sm_count);
-    mmvq_kernel<TYPE, B, T><<<grid, kThreads, smem, stream>>>(p);
+    mmvq_kernel<TYPE, B, T><<<grid, kThreads, smem, stream>>>(p, tmap);
     GGB_CUDA_TRY(cudaGetLastError());
     return GGB_OK;
 }
@@ -509,6 +559,8 @@ int dispatch_dtype(const void *W, const void *X, void *Y, int dt, int64_t B, int
 }
 
 }  // namespace
+
+void ggb_mmvq_tune_tiled(int max_box_bytes) { g_max_box = max_box_bytes < 0 ? -1 : (max_box_bytes > 1024 ? 1024 : max_box_bytes); }
 
 // mmvq_mma.cu: tensor-core integer dots for batches >= 3 (returns 1 when it does not apply)
 int ggb_mmvq_mma_impl(const void *W, const void *X, void *Y, int type, int xy_dtype, int64_t B, int64_t K, int64_t N,

@@ -21,6 +21,8 @@ _capi.lib.ggb_set_option(2, warps | (cap << 8))
 if "mma" in opt:      # cs,s_log2+1,min_batch
     a, b, c = (int(v) for v in opt["mma"].split(","))
     _capi.lib.ggb_set_option(5, a | (b << 8) | (c << 16))
+if "tiled" in opt:    # largest TMA box of the generic kernel's tiled stages (0 = per-row bulk copies)
+    _capi.lib.ggb_set_option(6, int(opt["tiled"]))
 l2 = int(opt.get("l2", "0"))
 _capi.lib.ggb_set_option(4, l2)
 shapes = ((14336, 4096), (4096, 14336), (28672, 8192), (8192, 28672))
