@@ -101,8 +101,9 @@ def test_long_rows_k_phases(ops, case):
     _check(ops, t, N, K, B, torch.float32, seed=B + 1)
 
 
-@pytest.mark.parametrize("case", [(oracle.Q4_K, 1), (oracle.Q4_K, 2), (oracle.Q4_K, 5), (oracle.Q6_K, 8), (oracle.Q5_K, 3)],
-                         ids=["Q4_K-B1", "Q4_K-B2", "Q4_K-B5", "Q6_K-B8", "Q5_K-B3"])
+@pytest.mark.parametrize("case", [(oracle.Q4_K, 1), (oracle.Q4_K, 2), (oracle.Q4_K, 5), (oracle.Q6_K, 8), (oracle.Q5_K, 3),
+                                  (oracle.IQ4_XS, 2), (oracle.IQ4_XS, 6)],
+                         ids=["Q4_K-B1", "Q4_K-B2", "Q4_K-B5", "Q6_K-B8", "Q5_K-B3", "IQ4_XS-B2", "IQ4_XS-B6"])
 def test_gather_epilogue_single_gpu(ops, case):
     """ggb_mmvq_gather with two 'peer' buffers on one GPU: every result lands at [tok, col_offset + row] of BOTH
     buffers, bit-identical to the plain op; nothing outside the slice is touched."""
