@@ -98,3 +98,21 @@ def test_fake_tensor_shapes():
         assert d.shape == (8, 256) and d.dtype == torch.float16
         v = torch.ops.ggml_b200.ggml_mul_mat_vec_a8(W, X[0, :2], 12, 8)
         assert v.shape == (2, 8)
+
+
+def test_iq4_types_and_options_without_gpu(capi):
+    """IQ4_NL / IQ4_XS: geometry known, MMQ refused (like the reference, which has no MMQ case for them); every tuning
+    option is accepted and restored, an unknown one is an argument error."""
+    L = capi.lib
+    assert (L.ggb_block_elems(20), L.ggb_block_bytes(20)) == (32, 18)
+    assert (L.ggb_block_elems(23), L.ggb_block_bytes(23)) == (256, 136)
+    buf = ctypes.create_string_buffer(8192)
+    p16 = (ctypes.addressof(buf) + 255) & ~255
+    for t in (20, 23):
+        assert L.ggb_mmq(p16, p16, p16, t, capi.GGB_F16, 4, 256, 8, 8, p16, 1 << 20, None) == -1   # GGB_E_TYPE
+        assert b"MMVQ only" in L.ggb_last_error()
+        assert L.ggb_mmq_workspace_bytes(t, 4, 256, 8) == 0
+    for opt, val, restore in ((6, 0, -1), (6, 1024, -1), (4, 8, 0), (1, 1, 0)):
+        assert L.ggb_set_option(opt, val) == 0
+        assert L.ggb_set_option(opt, restore) == 0
+    assert L.ggb_set_option(99, 1) < 0
