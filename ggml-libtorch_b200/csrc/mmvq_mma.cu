@@ -406,6 +406,51 @@ __device__ __forceinline__ void q6_step(const uint8_t *r0, const uint8_t *r1, co
     acc[3] += d1 * (fs[3] - cm[3]);
 }
 
+// ---- IQ4_NL: 18-byte blocks {d, 16 bytes of 4-bit codebook indices} (dequantize.cuh:400-416, vecdotq.cuh:842-864).  Eight
+// blocks = 144 bytes are treated as the kernel's 256-value unit; a block's code words are 2-byte aligned (odd blocks
+// 4-byte aligned), its fp16 d is the sub-block scale.  Otherwise IQ4_XS's step.
+template <> struct MmaOps<T_IQ4_NL> {
+    static constexpr int BS = 144;
+    static constexpr bool S16 = false;
+    __device__ __forceinline__ static void step(const uint8_t *r0, const uint8_t *r1, const uint8_t *ap, const float2 *dp,
+                                                const float2 *, int *scr, int q, int t, float (&acc)[4]) {
+        float *fscr = reinterpret_cast<float *>(scr);
+        *reinterpret_cast<float2 *>(fscr + q * 8 + 2 * t) = make_float2(ggb_h2f(ld_u16(r0 + 18 * t)), ggb_h2f(ld_u16(r0 + 18 * (t + 4))));
+        *reinterpret_cast<float2 *>(fscr + (q + 8) * 8 + 2 * t) = make_float2(ggb_h2f(ld_u16(r1 + 18 * t)), ggb_h2f(ld_u16(r1 + 18 * (t + 4))));
+        __syncwarp();
+        float s0[8], s1[8];                                      // s0[2j] = block j, s0[2j+1] = block j + 4 (row q); s1: row q + 8
+        {
+            const float4 a = *reinterpret_cast<const float4 *>(fscr + q * 8), b = *reinterpret_cast<const float4 *>(fscr + q * 8 + 4);
+            const float4 c = *reinterpret_cast<const float4 *>(fscr + (q + 8) * 8), d = *reinterpret_cast<const float4 *>(fscr + (q + 8) * 8 + 4);
+            s0[0] = a.x; s0[1] = a.y; s0[2] = a.z; s0[3] = a.w; s0[4] = b.x; s0[5] = b.y; s0[6] = b.z; s0[7] = b.w;
+            s1[0] = c.x; s1[1] = c.y; s1[2] = c.z; s1[3] = c.w; s1[4] = d.x; s1[5] = d.y; s1[6] = d.z; s1[7] = d.w;
+        }
+        float fs[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int ib = 0; ib < 8; ib++) {
+            const uint32_t w0 = (ib & 1) ? ldw_a2<true>(r0 + 18 * ib + 2 + 4 * t) : ldw_a2<false>(r0 + 18 * ib + 2 + 4 * t);
+            const uint32_t w1 = (ib & 1) ? ldw_a2<true>(r1 + 18 * ib + 2 + 4 * t) : ldw_a2<false>(r1 + 18 * ib + 2 + 4 * t);
+            const uint32_t b0 = *reinterpret_cast<const uint32_t *>(ap + 32 * ib + 4 * t);
+            const uint32_t b1 = *reinterpret_cast<const uint32_t *>(ap + 32 * ib + 16 + 4 * t);
+            uint32_t a0, a1, a2, a3;
+            iq4nl_lut8(w0, a0, a2);
+            iq4nl_lut8(w1, a1, a3);
+            int c[4];
+            mma_s8(c, a0, a1, a2, a3, b0, b1);
+            const float2 d8 = dp[ib];
+            const int si = 2 * (ib & 3) + (ib >> 2);
+            fs[0] = fmaf(__int_as_float(c[0] + kMagicBits) - kMagic, d8.x * s0[si], fs[0]);
+            fs[1] = fmaf(__int_as_float(c[1] + kMagicBits) - kMagic, d8.y * s0[si], fs[1]);
+            fs[2] = fmaf(__int_as_float(c[2] + kMagicBits) - kMagic, d8.x * s1[si], fs[2]);
+            fs[3] = fmaf(__int_as_float(c[3] + kMagicBits) - kMagic, d8.y * s1[si], fs[3]);
+        }
+        acc[0] += fs[0];
+        acc[1] += fs[1];
+        acc[2] += fs[2];
+        acc[3] += fs[3];
+    }
+};
+
 template <> struct MmaOps<T_Q6_K> {
     static constexpr int BS = 210;
     static constexpr bool S16 = true;
@@ -754,7 +799,7 @@ bool mma_applies(int type, int64_t B, int64_t K) {
     // measured crossover with the dp4a kernel (Llama-8B shapes): batch 3 for K = 4096, batch 2 for the long rows, where
     // the dp4a kernel's per-CTA activation quantization (3.3 us at K = 14336) costs more than the image kernel's launch
     const int64_t min_b = (g_min_batch == 3 && K > 8192) ? 2 : g_min_batch;
-    return (type == T_Q4_K || type == T_Q5_K || type == T_Q6_K || type == T_IQ4_XS) && B >= min_b && B <= 8 && K % 256 == 0 && K <= (1 << 16);
+    return (type == T_Q4_K || type == T_Q5_K || type == T_Q6_K || type == T_IQ4_XS || type == T_IQ4_NL) && B >= min_b && B <= 8 && K % 256 == 0 && K <= (1 << 16);
 }
 
 }  // namespace
@@ -782,6 +827,7 @@ int ggb_mmvq_mma_impl(const void *W, const void *X, void *Y, int type, int xy_dt
         case T_Q5_K: rc = dispatch_dtype<T_Q5_K>(W, X, Y, xy_dtype, B, K, N, ws, stream); break;
         case T_Q6_K: rc = dispatch_dtype<T_Q6_K>(W, X, Y, xy_dtype, B, K, N, ws, stream); break;
         case T_IQ4_XS: rc = dispatch_dtype<T_IQ4_XS>(W, X, Y, xy_dtype, B, K, N, ws, stream); break;
+        case T_IQ4_NL: rc = dispatch_dtype<T_IQ4_NL>(W, X, Y, xy_dtype, B, K, N, ws, stream); break;
         default: return 1;
     }
     if (rc != 1 || B < 6 || ggb_current_yout() || ggb_current_xin()) return rc;
