@@ -187,6 +187,50 @@ def ref_custom_ops():
     return _ref_mod
 
 
+# ---------------------------------------------------------------- the reference's own CUDA ops (sm_100a build)
+
+_REF_CUDA_DIR = os.path.join(_HERE, "_ref_cuda")
+_ref_cuda = None
+
+
+class _RefCudaOps:
+    """torch.ops._ggml.* = the reference's three CUDA ops compiled unmodified for sm_100a (oracle/build_ref_cuda.py), plus
+    torch.ops._ggml_q8shim.* = its two file-static q8_1 quantizers (oracle/ref_cuda_q8_shim.cu)."""
+
+    def __init__(self, torch):
+        self._t = torch
+        self.ggml_dequantize = torch.ops._ggml.ggml_dequantize
+        self.ggml_mul_mat_vec_a8 = torch.ops._ggml.ggml_mul_mat_vec_a8
+        self.ggml_mul_mat_a8 = torch.ops._ggml.ggml_mul_mat_a8
+
+    def quantize_q8_1(self, X):
+        """uint8 [rows, Kp/32*36] exactly as quantize_row_q8_1_cuda leaves it (ggml_kernel.cu:52-66)."""
+        out = self._t.ops._ggml_q8shim.quantize_q8_1(X)
+        return out.view(self._t.uint8).reshape(X.shape[0], -1)
+
+    def quantize_q8_1_mmq(self, X, qtype: int):
+        """uint8 [Kp/128, rows, 144] exactly as quantize_mmq_q8_1_cuda leaves it (mmq.cu:157-177)."""
+        out = self._t.ops._ggml_q8shim.quantize_q8_1_mmq(X, int(qtype))
+        return out.view(self._t.uint8).reshape(-1, X.shape[0], 144)
+
+
+def ref_cuda_ops():
+    """The reference's CUDA ops built for sm_100a (oracle/_ref_cuda/*.so), or None when they are not built.
+    Test / bench-comparator infrastructure only.  Never builds on the GPU box (the reference tree is absent there)."""
+    global _ref_cuda
+    if _ref_cuda is None:
+        main, shim = os.path.join(_REF_CUDA_DIR, "_ggml.so"), os.path.join(_REF_CUDA_DIR, "_ggml_q8shim.so")
+        if not (os.path.exists(main) and os.path.exists(shim)):
+            return None
+        import torch
+        if not torch.cuda.is_available():
+            return None
+        torch.ops.load_library(main)
+        torch.ops.load_library(shim)
+        _ref_cuda = _RefCudaOps(torch)
+    return _ref_cuda
+
+
 # ---------------------------------------------------------------- synthetic GGUF weights
 
 def random_weights(qtype: int, rows: int, cols: int, seed: int = 0) -> np.ndarray:
