@@ -23,6 +23,7 @@ void ggb_mmq_tune(int nb);
 void ggb_mmvq_tune_tiled(int max_box_bytes);
 void ggb_mmvq_sb_set_l2_prefetch(int mb);
 void ggb_mmvq_mma_tune(int cs, int s_log2_plus1, int min_batch);
+void ggb_mmvq_rg_set_mode(int mode);
 int ggb_mmvq_mma_impl(const void *W, const void *X, void *Y, int type, int xy_dtype, int64_t B, int64_t K, int64_t N,
                       void *ws, int64_t ws_bytes, cudaStream_t stream);
 int ggb_mmvq_sb_impl(const void *W, const void *X, void *Y, int type, int xy_dtype, int64_t B, int64_t K, int64_t N,
@@ -125,6 +126,9 @@ int ggb_set_option(int option, int value) {
             return GGB_OK;
         case GGB_OPT_MMVQ_WARPS:
             ggb_mmvq_sb_tune(value & 0xff, value >> 8);
+            return GGB_OK;
+        case GGB_OPT_MMVQ_RG:
+            ggb_mmvq_rg_set_mode(value);
             return GGB_OK;
         default:
             ggb_set_error("ggb_set_option: unknown option %d", option);

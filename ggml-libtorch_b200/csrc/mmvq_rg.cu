@@ -1,0 +1,367 @@
+// mmvq_rg.cu -- batch-1 MMVQ with the q8_1 activations RESIDENT IN REGISTERS (Q4_K; K % 256 == 0, K <= 16384).
+//
+// Same contract as the other MMVQ kernels (ggml_mul_mat_vec_a8 = quantize_row_q8_1_cuda + mul_mat_vec_q + vec_dot_q4_K_q8_1,
+// hf-kernels/ggml-kernels/ggml/ggml_kernel.cu:13-66,80-193; ggml/mmvq.cuh:2-38; ggml/vecdotq.cuh:266-327).
+//
+// Why a second kernel next to mmvq_sb_body.cuh.  Round-1 measurements (profiles/r01_*) showed the half-SM ring
+// kernel CONSUMER-bound, not HBM-bound: its DRAM traffic equals the algorithmic bytes, but eight warps per SM at ~1
+// instruction per weight value (of which a quarter are shared-memory loads of the activations) run the stream phase at
+// just the HBM rate, so every microsecond the launch spends waiting for its dependency and quantizing X (2-3 us of an
+// 8.5 us period, per-CTA globaltimer traces) is lost.  Here the consumer is made ~2x faster than HBM so that the rings
+// pre-filled during that serial part are drained at shared-memory speed and the remainder streams at HBM speed:
+//   * a lane owns ONE 128-value item position of a row chunk (32 items = 4096 values) and keeps that item's q8_1
+//     activations (32 words of quants + 4 d8 + 4 d8*sum(q8)) in REGISTERS for the whole launch: no activation loads in the
+//     main loop (5 LDS.128 per 128 weights instead of 15), ~0.6 instructions per weight value;
+//   * 12 warps in a half-SM CTA (<= 80 registers, <= 113 KB): three warps per scheduler, and still two CTAs per SM so that
+//     the NEXT launch (programmatic dependent launch) is resident and pre-fills its rings while this one runs;
+//   * a slot is one row chunk (<= 2304 B): finer work granularity (shorter tail), per-warp self-refilling rings as before;
+//   * rows longer than 4096 values are split into chunks owned by different warps (warp w: chunk w % C); the chunk
+//     partials of a row meet in shared memory and are added in chunk order at the end, so the summation order depends on
+//     K only (N-sharded results stay bit-identical);
+//   * four rows are reduced at once (6 shuffles per 4 rows instead of 20).
+// The activation quantization itself is unchanged (q8_1.cuh: bit-identical to quantize_q8_1).
+#include "q8_1.cuh"
+
+namespace ggb_sb {
+extern int g_pdl_prefetch;
+int g_rg_mode = 0;           // ggb_set_option(GGB_OPT_MMVQ_RG): bit 0 = use this kernel; bits 8.. = debug (1 = skip quantization, 2 = skip the dots)
+}
+unsigned long long *ggb_mmvq_trace_slot();
+
+namespace {
+
+constexpr int kNW = 12;                  // warps per CTA
+constexpr int kChunkItems = 32;          // items (128 values) per row chunk = one per lane
+
+struct RgParams {
+    const uint8_t *W;
+    const void *X;
+    GgbXIn xin;
+    GgbYOut yo;
+    int64_t N;
+    int K, nsb, ipr, row_bytes;
+    int C;               // chunks per row
+    int RW;              // row lanes per CTA = kNW / C
+    int off_scales, off_part, off_slots;
+    int early;           // rows per warp requested before the dependency wait (static weights), 1..kStages
+    int part_rows;       // rows the partial-sum area holds (C > 1)
+    int x_vec;
+    int pdl_prefetch;
+    int dbg;
+    unsigned long long *trace;
+};
+
+__device__ __forceinline__ int dp4a_ss(uint32_t a, uint32_t b, int c) { return __dp4a((int)a, (int)b, c); }
+__device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// exact (float)(a * b) for |a * b| < 2^22
+__device__ __forceinline__ float imul_to_f32(int a, int b) { return __int_as_float(a * b + 0x4B400000) - 12582912.0f; }
+template <int J>
+__device__ __forceinline__ float byte_to_f32(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540 + J)) - 8388608.0f; }
+template <int J>
+__device__ __forceinline__ int byte_of(uint32_t w) { return (int)__byte_perm(w, 0, 0x4440 + J); }
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+template <int TYPE> struct RgOps;
+
+// ---- Q4_K: one 128-value item (half h of a 144-byte super-block) against the lane's resident activations
+template <> struct RgOps<T_Q4_K> {
+    static constexpr int BS = 144;
+    // rec: this lane's record of the row, pieces 32 uint4 apart: [0] the super-block header, [1..4] the item's 64 nibble bytes
+    __device__ __forceinline__ static float item(const uint4 *rec, const uint32_t (&a)[32], const float4 d8, const float4 ds, int h) {
+        const uint4 hd = rec[0];
+        const uint4 q0 = rec[32], q1 = rec[64], q2 = rec[96], q3 = rec[128];
+        const float2 dm = __half22float2(*reinterpret_cast<const __half2 *>(&hd.x));
+        // (scale, min) of the item's four 32-value groups, one per byte (dequantize.cuh:154-161)
+        uint32_t sc, mn;
+        if (h) {
+            sc = (hd.w & 0x0f0f0f0fu) | ((hd.y >> 2) & 0x30303030u);
+            mn = ((hd.w >> 4) & 0x0f0f0f0fu) | ((hd.z >> 2) & 0x30303030u);
+        } else {
+            sc = hd.y & 0x3f3f3f3fu;
+            mn = hd.z & 0x3f3f3f3fu;
+        }
+        // bytes 0..31 of the item: low nibbles = group 0 (a[0..7]), high nibbles = group 1 (a[8..15]); bytes 32..63: groups 2, 3
+        const uint32_t qa[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        const uint32_t qb[8] = {q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+        int g0 = 0, g0b = 0, g1 = 0, g1b = 0, g2 = 0, g2b = 0, g3 = 0, g3b = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            g0 = dp4a_ss(qa[i] & 0x0f0f0f0fu, a[i], g0);
+            g0b = dp4a_ss(qa[i + 4] & 0x0f0f0f0fu, a[i + 4], g0b);
+            g1 = dp4a_us(qa[i] & 0xf0f0f0f0u, a[8 + i], g1);               // 16 x the high nibbles
+            g1b = dp4a_us(qa[i + 4] & 0xf0f0f0f0u, a[12 + i], g1b);
+            g2 = dp4a_ss(qb[i] & 0x0f0f0f0fu, a[16 + i], g2);
+            g2b = dp4a_ss(qb[i + 4] & 0x0f0f0f0fu, a[20 + i], g2b);
+            g3 = dp4a_us(qb[i] & 0xf0f0f0f0u, a[24 + i], g3);
+            g3b = dp4a_us(qb[i + 4] & 0xf0f0f0f0u, a[28 + i], g3b);
+        }
+        float fd = d8.x * imul_to_f32(g0 + g0b, byte_of<0>(sc));
+        fd = fmaf(d8.y, imul_to_f32((g1 + g1b) >> 4, byte_of<1>(sc)), fd);
+        fd = fmaf(d8.z, imul_to_f32(g2 + g2b, byte_of<2>(sc)), fd);
+        fd = fmaf(d8.w, imul_to_f32((g3 + g3b) >> 4, byte_of<3>(sc)), fd);
+        // minima: dmin * sum_g m_g * (d8_g * sum q8_g)    (vecdotq.cuh:280-288)
+        float t = byte_to_f32<0>(mn) * ds.x;
+        t = fmaf(byte_to_f32<1>(mn), ds.y, t);
+        t = fmaf(byte_to_f32<2>(mn), ds.z, t);
+        t = fmaf(byte_to_f32<3>(mn), ds.w, t);
+        return dm.x * fd - dm.y * t;
+    }
+};
+
+// 16-byte asynchronous copy global -> shared (LDGSTS), L2 only, evict-first: the lane's own piece of a weight row
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, uint64_t policy) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Weight pipeline: every lane copies ITS OWN 80 bytes of a row chunk (the 16-byte super-block header and the 64 bytes of
+// nibbles of its item) with five 16-byte cp.async into a private record [stage][part][lane] of shared memory and reads them
+// back with five conflict-free LDS.128.  Nothing is shared between lanes, so there are no barriers at all in the main
+// loop: cp.async groups are per thread (one group per row, D rows in flight per warp).  (Measured first, scripts/probes/
+// stream_probe.cu: a cp.async.bulk per 2304-byte row chunk caps the stream at ~5.1 TB/s -- the TMA unit spends ~115
+// cycles per request -- while plain 16-byte-per-lane loads reach 7.1 TB/s.)
+constexpr int kStages = 3;               // rows in flight per warp
+constexpr int kParts = 5;                // 16-byte pieces per lane and row (Q4_K: header + 4 x nibbles)
+
+template <int TYPE, typename T>
+__global__ void __launch_bounds__(kNW * 32, 2)
+mmvq_rg_kernel(const RgParams p) {
+    using Ops = RgOps<TYPE>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint4 *act_q = reinterpret_cast<uint4 *>(smem);                            // [8][ipr]: 16-value chunk i of item it at i * ipr + it
+    float4 *act_s = reinterpret_cast<float4 *>(smem + p.off_scales);           // [2][ipr]: d8 of the item's 4 groups | d8 * sum(q8)
+    float *part_sm = reinterpret_cast<float *>(smem + p.off_part);             // [part_rows][C] chunk partials (C > 1)
+    uint4 *ring = reinterpret_cast<uint4 *>(smem + p.off_slots);               // [warp][stage][part][lane]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ipr = p.ipr, C = p.C, RW = p.RW;
+
+    const int64_t r_begin = p.N * (int64_t)blockIdx.x / gridDim.x;
+    const int64_t r_end = p.N * (int64_t)(blockIdx.x + 1) / gridDim.x;
+    const int nrows = (int)(r_end - r_begin);
+
+    if (p.trace && tid == 0) p.trace[blockIdx.x * 4 + 0] = gtime();
+    ggb_pdl_launch_dependents();
+
+    // warp -> (chunk c, row lane rl): rows rl, rl + RW, ... of this CTA's range, chunk c of each
+    const int c = warp % C, rl = warp / C;
+    const int my_rows = (rl < RW && nrows > rl) ? (nrows - rl + RW - 1) / RW : 0;
+    const int item = c * kChunkItems + lane;
+    const bool live = item < ipr;
+    const int h = lane & 1;
+    // this lane's pieces of a row: the header of super-block item / 2 and the nibbles of half h
+    const uint8_t *wsrc = p.W + (r_begin + rl) * (int64_t)p.row_bytes + (int64_t)(item >> 1) * Ops::BS;
+    const int64_t wstep = (int64_t)RW * p.row_bytes;
+    uint4 *my_ring = ring + (warp * kStages * kParts) * 32 + lane;
+    const uint64_t pol = l2_policy_evict_first();
+
+    int is_k = 0;
+    auto issue_row = [&]() {                     // row is_k of this warp -> stage is_k % kStages (an empty group past the end)
+        if (live && is_k < my_rows) {
+            const uint8_t *src = wsrc + (int64_t)is_k * wstep;
+            uint4 *dst = my_ring + ((is_k % kStages) * kParts) * 32;
+            cp_async16(dst, src, pol);
+            const uint8_t *qs = src + 16 + 64 * h;
+#pragma unroll
+            for (int q = 0; q < 4; q++) cp_async16(dst + (1 + q) * 32, qs + 16 * q, pol);
+        }
+        cp_async_commit();
+        is_k++;
+    };
+    // static weights: the first rows are requested while the previous kernel of the stream still runs.  Only p.early of
+    // the kStages rows: this SM's requests are served in order, and the other CTA of the SM (the PREVIOUS launch) is about
+    // to read its activations -- a deep burst here would sit in front of that latency-critical read.
+    const int early = p.pdl_prefetch ? p.early : 0;
+    for (int s = 0; s < early; s++) issue_row();
+    ggb_pdl_wait();
+    if (p.trace && tid == 0) p.trace[blockIdx.x * 4 + 1] = gtime();
+
+    // ===================== q8_1-quantize X into shared memory (bit-identical to quantize_q8_1) =====================
+    const T *X = static_cast<const T *>(p.X);
+    const int ngroups_row = p.K >> 5;
+    const int t4 = lane & 3;
+    constexpr int GPI = (kNW * 32) / 4;
+    constexpr int U = 2;
+    for (int base = 0; base < ngroups_row; base += U * GPI) {
+        float v[U][8];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int g = base + u * GPI + (tid >> 2);
+            if (g < ngroups_row && !(p.dbg & 1)) {
+                load_act8<T>(X, static_cast<const T *>(p.xin.x2), p.xin.ldx, 0, g * 32 + t4 * 8, p.x_vec != 0, v[u]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; i++) v[u][i] = 0.0f;
+            }
+        }
+        // the rest of the weight pipeline goes out BEHIND the first activation loads
+        if (base == 0)
+            for (int s = early; s < kStages; s++) issue_row();
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (base + u * GPI >= ngroups_row) break;             // warp-uniform
+            const int g = base + u * GPI + (tid >> 2);
+            const Q8Group q = q8_1_quantize_group<false>(v[u]);
+            int mine = __dp4a((int)q.q_lo, 0x01010101, __dp4a((int)q.q_hi, 0x01010101, 0));
+            mine += __shfl_xor_sync(0xffffffffu, mine, 1);
+            const int other = __shfl_xor_sync(0xffffffffu, mine, 2);
+            if (g < ngroups_row) {
+                const int it = g >> 2, j = g & 3;
+                const int i = 2 * j + (t4 >> 1);
+                uint8_t *dst = reinterpret_cast<uint8_t *>(act_q + i * ipr + it) + 8 * (t4 & 1);
+                *reinterpret_cast<uint2 *>(dst) = make_uint2(q.q_lo, q.q_hi);
+                if (t4 == 0) {
+                    const float d8 = __half2float(__float2half_rn(q.d));
+                    reinterpret_cast<float *>(act_s + it)[j] = d8;
+                    reinterpret_cast<float *>(act_s + ipr + it)[j] = d8 * (float)(mine + other);
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // this lane's item of every row chunk it will see: activations -> registers
+    uint32_t a[32];
+    float4 d8 = make_float4(0.f, 0.f, 0.f, 0.f), ds = d8;
+    if (live) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint4 v = act_q[i * ipr + item];
+            a[4 * i] = v.x; a[4 * i + 1] = v.y; a[4 * i + 2] = v.z; a[4 * i + 3] = v.w;
+        }
+        d8 = act_s[item];
+        ds = act_s[ipr + item];
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; i++) a[i] = 0u;
+    }
+    if (p.trace && tid == 0) p.trace[blockIdx.x * 4 + 2] = gtime();
+
+    // ===================== main loop: one step = chunk c of this warp's next row =====================
+    const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
+    float part[4] = {0.f, 0.f, 0.f, 0.f};
+    int stage = 0;
+    for (int j0 = 0; j0 < my_rows; j0 += 4) {
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) {
+            part[jj] = 0.0f;
+            if (j0 + jj < my_rows) {                                   // warp-uniform
+                cp_async_wait<kStages - 1>();                          // this thread's oldest row has landed
+                if (live && !(p.dbg & 2)) part[jj] = Ops::item(my_ring + (stage * kParts) * 32, a, d8, ds, h);
+                issue_row();                                           // refill the stage just consumed
+                if (++stage == kStages) stage = 0;
+            }
+        }
+        // four rows reduced together: xor 16 and xor 8 fold the four values onto the four lane octets, then 4, 2, 1.
+        // Every row's sum is the same fixed tree whatever its position in the group (fp32 add is commutative).
+        float x0 = (up16 ? part[2] : part[0]) + __shfl_xor_sync(0xffffffffu, up16 ? part[0] : part[2], 16);
+        float x1 = (up16 ? part[3] : part[1]) + __shfl_xor_sync(0xffffffffu, up16 ? part[1] : part[3], 16);
+        float v = (up8 ? x1 : x0) + __shfl_xor_sync(0xffffffffu, up8 ? x0 : x1, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        const int jr = j0 + (up16 ? 2 : 0) + (up8 ? 1 : 0);            // the row this lane octet holds
+        if ((lane & 7) == 0 && jr < my_rows) {
+            const int lr = rl + jr * RW;                               // row inside the CTA's range
+            if (C == 1) ggb_yout_store<T>(p.yo, 0, r_begin + lr, v);
+            else part_sm[lr * C + c] = v;
+        }
+    }
+    cp_async_wait<0>();
+    if (C > 1) {
+        __syncthreads();
+        for (int lr = tid; lr < nrows; lr += kNW * 32) {
+            float s = part_sm[lr * C];
+            for (int cc = 1; cc < C; cc++) s += part_sm[lr * C + cc];
+            ggb_yout_store<T>(p.yo, 0, r_begin + lr, s);
+        }
+    }
+    if (p.trace && tid == 0) p.trace[blockIdx.x * 4 + 3] = gtime();
+}
+
+template <int TYPE, typename T>
+int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, cudaStream_t stream) {
+    using Ops = RgOps<TYPE>;
+    const DeviceInfo &di = ggb_device_info();
+    RgParams p;
+    p.W = static_cast<const uint8_t *>(W);
+    p.X = X;
+    p.yo = ggb_make_yout(Y, N);
+    p.xin = ggb_make_xin(K);
+    p.N = N;
+    p.K = (int)K;
+    p.nsb = (int)(K / 256);
+    p.ipr = 2 * p.nsb;
+    p.row_bytes = p.nsb * Ops::BS;
+    p.C = (p.ipr + kChunkItems - 1) / kChunkItems;
+    if (p.C > 4 || kNW % p.C != 0 || p.row_bytes % 16 != 0) return 1;
+    p.RW = kNW / p.C;
+    p.x_vec = (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.xin.x2) & 15) == 0 &&
+              (p.xin.ldx * (int64_t)sizeof(T)) % 16 == 0;
+    p.pdl_prefetch = ggb_sb::g_pdl_prefetch;
+    p.dbg = (ggb_sb::g_rg_mode >> 8) & 0xff;
+    p.early = (ggb_sb::g_rg_mode >> 16) & 0xf;
+    if (p.early == 0 || p.early > kStages) p.early = 2;
+    const int64_t max_ctas = (N + p.RW - 1) / p.RW;
+    const int grid = (int)(max_ctas < di.sm_count ? max_ctas : di.sm_count);
+    p.part_rows = p.C > 1 ? (int)((N + grid - 1) / grid + 1) : 0;
+    if ((int64_t)p.part_rows * p.C * 4 > 16384) return 1;
+    p.off_scales = ((int)K + 15) & ~15;
+    p.off_part = p.off_scales + 2 * p.ipr * 16;
+    p.off_slots = (p.off_part + p.part_rows * p.C * 4 + 127) & ~127;
+    const int smem = p.off_slots + kNW * kStages * kParts * 512;
+    if (smem > (di.max_smem_optin + 1024) / 2 - 1024) return 1;               // two CTAs per SM
+    p.trace = ggb_mmvq_trace_slot();
+
+    static bool attr_set[64] = {};               // per instantiation and device; idempotent, so a race is harmless
+    if (!attr_set[di.dev]) {
+        GGB_CUDA_TRY(cudaFuncSetAttribute(mmvq_rg_kernel<TYPE, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin));
+        attr_set[di.dev] = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kNW * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmvq_rg_kernel<TYPE, T>, p));
+    return GGB_OK;
+}
+
+template <int TYPE>
+int dispatch_dtype(const void *W, const void *X, void *Y, int dt, int64_t K, int64_t N, cudaStream_t stream) {
+    switch (dt) {
+        case GGB_F32:  return launch<TYPE, float>(W, X, Y, K, N, stream);
+        case GGB_F16:  return launch<TYPE, __half>(W, X, Y, K, N, stream);
+        case GGB_BF16: return launch<TYPE, __nv_bfloat16>(W, X, Y, K, N, stream);
+        default: return 1;
+    }
+}
+
+}  // namespace
+
+void ggb_mmvq_rg_set_mode(int mode) { ggb_sb::g_rg_mode = mode; }
+
+// returns GGB_OK / a negative status, or 1 when this kernel does not apply (the caller goes on to mmvq_sb / mmvq)
+int ggb_mmvq_rg_impl(const void *W, const void *X, void *Y, int type, int xy_dtype, int64_t B, int64_t K, int64_t N,
+                     cudaStream_t stream) {
+    if (!(ggb_sb::g_rg_mode & 1) || B != 1 || K % 256 != 0 || K > 16384 || (reinterpret_cast<uintptr_t>(W) & 15)) return 1;
+    switch (type) {
+        case T_Q4_K: return dispatch_dtype<T_Q4_K>(W, X, Y, xy_dtype, K, N, stream);
+        default: return 1;
+    }
+}

@@ -47,10 +47,18 @@ GGB_SB_RUN(ggb_mmvq_sb_run_q5k);
 GGB_SB_RUN(ggb_mmvq_sb_run_q6k);
 GGB_SB_RUN(ggb_mmvq_sb_run_iq4xs);
 
+// mmvq_rg.cu: batch 1 with register-resident activations (returns 1 when it does not apply)
+int ggb_mmvq_rg_impl(const void *W, const void *X, void *Y, int type, int xy_dtype, int64_t B, int64_t K, int64_t N,
+                     cudaStream_t stream);
+
 // returns GGB_OK / a negative status, or 1 when this path does not apply (the caller uses mmvq.cu)
 int ggb_mmvq_sb_impl(const void *W, const void *X, void *Y, int type, int xy_dtype, int64_t B, int64_t K, int64_t N,
                      cudaStream_t stream) {
     if (K % 256 != 0 || K > (1 << 20) || (reinterpret_cast<uintptr_t>(W) & 15)) return 1;
+    {
+        const int rc = ggb_mmvq_rg_impl(W, X, Y, type, xy_dtype, B, K, N, stream);
+        if (rc != 1) return rc;
+    }
     switch (type) {
         case T_Q4_K: return ggb_mmvq_sb_run_q4k(W, X, Y, xy_dtype, B, K, N, stream);
         case T_Q5_K: return ggb_mmvq_sb_run_q5k(W, X, Y, xy_dtype, B, K, N, stream);

@@ -11,6 +11,7 @@ N, K, t, B = int(opt.get("N", 14336)), int(opt.get("K", 4096)), int(opt.get("t",
 L = _capi.lib
 L.ggb_set_option(1, static); L.ggb_set_option(2, warps | (cap << 8))
 l2 = int(opt.get("l2", "0")); L.ggb_set_option(4, l2)
+L.ggb_set_option(7, int(opt.get("rg", "0")))
 L.ggb_debug_mmvq_trace.argtypes = [ctypes.c_void_p]
 dev = torch.device("cuda")
 base = torch.from_numpy(synth.random_blocks(t, N, K, seed=1)).to(dev)
