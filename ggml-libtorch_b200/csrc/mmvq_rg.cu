@@ -20,11 +20,13 @@
 //     K only (N-sharded results stay bit-identical);
 //   * four rows are reduced at once (6 shuffles per 4 rows instead of 20).
 // The activation quantization itself is unchanged (q8_1.cuh: bit-identical to quantize_q8_1).
+#include <type_traits>
+
 #include "q8_1.cuh"
 
 namespace ggb_sb {
 extern int g_pdl_prefetch;
-int g_rg_mode = 0;           // ggb_set_option(GGB_OPT_MMVQ_RG): bit 0 = use this kernel; bits 8.. = debug (1 = skip quantization, 2 = skip the dots)
+int g_rg_mode = 1;           // ggb_set_option(GGB_OPT_MMVQ_RG): bit 0 = use this kernel; bits 8.. = debug (1 = skip quantization); bits 16..19 early stages; bits 20..27 rows pulled into L2 up front
 }
 unsigned long long *ggb_mmvq_trace_slot();
 
@@ -43,7 +45,9 @@ struct RgParams {
     int C;               // chunks per row
     int RW;              // row lanes per CTA = kNW / C
     int off_scales, off_part, off_slots;
+    int spc;             // super-blocks per chunk
     int early;           // rows per warp requested before the dependency wait (static weights), 1..kStages
+    long long wstep;     // bytes between two consecutive rows of a warp = RW * row_bytes
     int part_rows;       // rows the partial-sum area holds (C > 1)
     int x_vec;
     int pdl_prefetch;
@@ -69,15 +73,23 @@ __device__ __forceinline__ unsigned long long gtime() {
     return t;
 }
 
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+
 template <int TYPE> struct RgOps;
 
 // ---- Q4_K: one 128-value item (half h of a 144-byte super-block) against the lane's resident activations
 template <> struct RgOps<T_Q4_K> {
     static constexpr int BS = 144;
-    // rec: this lane's record of the row, pieces 32 uint4 apart: [0] the super-block header, [1..4] the item's 64 nibble bytes
-    __device__ __forceinline__ static float item(const uint4 *rec, const uint32_t (&a)[32], const float4 d8, const float4 ds, int h) {
-        const uint4 hd = rec[0];
-        const uint4 q0 = rec[32], q1 = rec[64], q2 = rec[96], q3 = rec[128];
+    // hdp: the lane's super-block header in the ring stage (the chunk's bytes as they lie in memory); qsp: the 64 bytes of
+    // nibbles of its half h (32-bit shared-memory addresses)
+    __device__ __forceinline__ static float item(uint32_t hdp, uint32_t qsp, const uint32_t (&a)[32], const float4 d8,
+                                                 const float4 ds, int h) {
+        const uint4 hd = lds128(hdp);
+        const uint4 q0 = lds128(qsp), q1 = lds128(qsp + 16), q2 = lds128(qsp + 32), q3 = lds128(qsp + 48);
         const float2 dm = __half22float2(*reinterpret_cast<const __half2 *>(&hd.x));
         // (scale, min) of the item's four 32-value groups, one per byte (dequantize.cuh:154-161)
         uint32_t sc, mn;
@@ -91,22 +103,18 @@ template <> struct RgOps<T_Q4_K> {
         // bytes 0..31 of the item: low nibbles = group 0 (a[0..7]), high nibbles = group 1 (a[8..15]); bytes 32..63: groups 2, 3
         const uint32_t qa[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
         const uint32_t qb[8] = {q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
-        int g0 = 0, g0b = 0, g1 = 0, g1b = 0, g2 = 0, g2b = 0, g3 = 0, g3b = 0;
+        int g0 = 0, g1 = 0, g2 = 0, g3 = 0;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
+        for (int i = 0; i < 8; i++) {
             g0 = dp4a_ss(qa[i] & 0x0f0f0f0fu, a[i], g0);
-            g0b = dp4a_ss(qa[i + 4] & 0x0f0f0f0fu, a[i + 4], g0b);
             g1 = dp4a_us(qa[i] & 0xf0f0f0f0u, a[8 + i], g1);               // 16 x the high nibbles
-            g1b = dp4a_us(qa[i + 4] & 0xf0f0f0f0u, a[12 + i], g1b);
             g2 = dp4a_ss(qb[i] & 0x0f0f0f0fu, a[16 + i], g2);
-            g2b = dp4a_ss(qb[i + 4] & 0x0f0f0f0fu, a[20 + i], g2b);
             g3 = dp4a_us(qb[i] & 0xf0f0f0f0u, a[24 + i], g3);
-            g3b = dp4a_us(qb[i + 4] & 0xf0f0f0f0u, a[28 + i], g3b);
         }
-        float fd = d8.x * imul_to_f32(g0 + g0b, byte_of<0>(sc));
-        fd = fmaf(d8.y, imul_to_f32((g1 + g1b) >> 4, byte_of<1>(sc)), fd);
-        fd = fmaf(d8.z, imul_to_f32(g2 + g2b, byte_of<2>(sc)), fd);
-        fd = fmaf(d8.w, imul_to_f32((g3 + g3b) >> 4, byte_of<3>(sc)), fd);
+        float fd = d8.x * imul_to_f32(g0, byte_of<0>(sc));
+        fd = fmaf(d8.y, imul_to_f32(g1 >> 4, byte_of<1>(sc)), fd);
+        fd = fmaf(d8.z, imul_to_f32(g2, byte_of<2>(sc)), fd);
+        fd = fmaf(d8.w, imul_to_f32(g3 >> 4, byte_of<3>(sc)), fd);
         // minima: dmin * sum_g m_g * (d8_g * sum q8_g)    (vecdotq.cuh:280-288)
         float t = byte_to_f32<0>(mn) * ds.x;
         t = fmaf(byte_to_f32<1>(mn), ds.y, t);
@@ -116,24 +124,38 @@ template <> struct RgOps<T_Q4_K> {
     }
 };
 
-// 16-byte asynchronous copy global -> shared (LDGSTS), L2 only, evict-first: the lane's own piece of a weight row
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, uint64_t policy) {
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "l"(policy) : "memory");
+// 16-byte asynchronous copy global -> shared (LDGSTS), L2 only, evict-first
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void *gsrc, uint64_t policy) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "l"(policy) : "memory");
+}
+// the same, predicated on (have > need): a branch around an LDGSTS costs ptxas 12.9 three padding instructions and a BSSY/BSYNC pair
+__device__ __forceinline__ void cp_async16_if(int have, int need, uint32_t smem_dst, const void *gsrc, uint64_t policy) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.gt.s32 p, %3, %4;\n\t"
+                 "@p cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n\t}"
+                 ::"r"(smem_dst), "l"(gsrc), "l"(policy), "r"(have), "r"(need) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ long long clk64() {
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));
+    return t;
+}
 
-// Weight pipeline: every lane copies ITS OWN 80 bytes of a row chunk (the 16-byte super-block header and the 64 bytes of
-// nibbles of its item) with five 16-byte cp.async into a private record [stage][part][lane] of shared memory and reads them
-// back with five conflict-free LDS.128.  Nothing is shared between lanes, so there are no barriers at all in the main
-// loop: cp.async groups are per thread (one group per row, D rows in flight per warp).  (Measured first, scripts/probes/
-// stream_probe.cu: a cp.async.bulk per 2304-byte row chunk caps the stream at ~5.1 TB/s -- the TMA unit spends ~115
-// cycles per request -- while plain 16-byte-per-lane loads reach 7.1 TB/s.)
-constexpr int kStages = 3;               // rows in flight per warp
-constexpr int kParts = 5;                // 16-byte pieces per lane and row (Q4_K: header + 4 x nibbles)
-
-template <int TYPE, typename T>
+// Weight pipeline.  A warp owns chunk c (<= 16 super-blocks = <= 2304 contiguous bytes) of rows rl, rl + RW, ... and keeps
+// S of those row chunks in flight in a private ring.  The copy is COALESCED: the warp moves the chunk as consecutive
+// 16-byte pieces (lane l: pieces l, l + 32, ...; cp.async.cg = LDGSTS, no registers, no L1), the image in shared memory is
+// the chunk's bytes as they are, and every lane then reads ITS item (header + 64 bytes of nibbles, five conflict-free
+// LDS.128: super-blocks are 144 = 128 + 16 bytes apart).  cp.async groups are per thread: wait_group + __syncwarp make
+// the whole chunk visible to the warp; there is no CTA-wide synchronisation in the main loop.
+// (Measured first, scripts/probes/stream_probe.cu: a cp.async.bulk per 2304-byte chunk caps the stream at ~5.1 TB/s -- the
+// TMA unit takes ~115 cycles per request whatever its size -- while coalesced 16-byte-per-lane loads reach 7.1 TB/s; and
+// lane-private pieces (every lane copying its own 5 x 16 bytes) touch every 32-byte sector twice: 12.4 us instead of 8.)
+// S = row chunks in flight per warp (ring stages): 4 where the ring fits beside the activations in half an SM's shared
+// memory (K = 4096: 12 warps x 4 x 2304 B + 5 KB = exactly the 113 KB two resident CTAs may have each), else 3.
+// FULL = every chunk has 16 super-blocks (K % 4096 == 0): all lanes own an item and the copy needs no bounds.
+template <int TYPE, typename T, int S, bool FULL>
 __global__ void __launch_bounds__(kNW * 32, 2)
 mmvq_rg_kernel(const RgParams p) {
     using Ops = RgOps<TYPE>;
@@ -141,7 +163,7 @@ mmvq_rg_kernel(const RgParams p) {
     uint4 *act_q = reinterpret_cast<uint4 *>(smem);                            // [8][ipr]: 16-value chunk i of item it at i * ipr + it
     float4 *act_s = reinterpret_cast<float4 *>(smem + p.off_scales);           // [2][ipr]: d8 of the item's 4 groups | d8 * sum(q8)
     float *part_sm = reinterpret_cast<float *>(smem + p.off_part);             // [part_rows][C] chunk partials (C > 1)
-    uint4 *ring = reinterpret_cast<uint4 *>(smem + p.off_slots);               // [warp][stage][part][lane]
+    uint8_t *ring = smem + p.off_slots;                                        // [warp][stage][stage_bytes]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ipr = p.ipr, C = p.C, RW = p.RW;
@@ -150,49 +172,73 @@ mmvq_rg_kernel(const RgParams p) {
     const int64_t r_end = p.N * (int64_t)(blockIdx.x + 1) / gridDim.x;
     const int nrows = (int)(r_end - r_begin);
 
-    if (p.trace && tid == 0) p.trace[blockIdx.x * 4 + 0] = gtime();
+    unsigned long long *tr = p.trace ? p.trace + blockIdx.x * 8 : nullptr;
+    if (tr && tid == 0) { tr[7] = gtime(); tr[0] = clk64(); }
     ggb_pdl_launch_dependents();
 
     // warp -> (chunk c, row lane rl): rows rl, rl + RW, ... of this CTA's range, chunk c of each
     const int c = warp % C, rl = warp / C;
     const int my_rows = (rl < RW && nrows > rl) ? (nrows - rl + RW - 1) / RW : 0;
-    const int item = c * kChunkItems + lane;
-    const bool live = item < ipr;
-    const int h = lane & 1;
-    // this lane's pieces of a row: the header of super-block item / 2 and the nibbles of half h
-    const uint8_t *wsrc = p.W + (r_begin + rl) * (int64_t)p.row_bytes + (int64_t)(item >> 1) * Ops::BS;
-    const int64_t wstep = (int64_t)RW * p.row_bytes;
-    uint4 *my_ring = ring + (warp * kStages * kParts) * 32 + lane;
+    const int sb0 = c * p.spc;                                   // first super-block of the chunk
+    const int nsb_c = FULL ? 16 : min(p.spc, p.nsb - sb0);       // super-blocks in it
+    const int n16 = nsb_c * (Ops::BS / 16);                      // 16-byte pieces per row chunk
+    const int sbl = lane >> 1, h = lane & 1;                     // this lane's item: half h of super-block sb0 + sbl
+    const bool live = FULL || sbl < nsb_c;
+    const int item = 2 * (sb0 + sbl) + h;
+    // a stage is always 16 super-blocks wide, whatever the chunk holds: every shared-memory offset is an immediate.  (With a
+    // run-time stage size ptxas 12.9 encoded the LDGSTS whose shared address is register + uniform register with an
+    // unset uniform register and descriptor: illegal instruction at run time.)
+    constexpr int stage_bytes = 16 * Ops::BS;
+    uint8_t *my_ring = ring + (size_t)warp * S * stage_bytes;
+    const uint32_t my_ring_s = smem_u32(my_ring) + lane * 16;    // (32-bit shared address computed once: with the generic
+                                                                 // -> shared conversion inside the copy loop ptxas 12.9 emitted an
+                                                                 // LDGSTS with a bad descriptor register: illegal instruction)
     const uint64_t pol = l2_policy_evict_first();
 
-    int is_k = 0;
-    auto issue_row = [&]() {                     // row is_k of this warp -> stage is_k % kStages (an empty group past the end)
-        if (live && is_k < my_rows) {
-            const uint8_t *src = wsrc + (int64_t)is_k * wstep;
-            uint4 *dst = my_ring + ((is_k % kStages) * kParts) * 32;
-            cp_async16(dst, src, pol);
-            const uint8_t *qs = src + 16 + 64 * h;
-#pragma unroll
-            for (int q = 0; q < 4; q++) cp_async16(dst + (1 + q) * 32, qs + 16 * q, pol);
+    // this lane's pieces of a row chunk: lane, lane + 32, ... (npc of them).  The source advances by one row per request.
+    const int npc = (n16 - lane + 31) >> 5;
+    const int lo16 = lane < 16;
+    const uint8_t *src_next = p.W + (r_begin + rl) * (int64_t)p.row_bytes + (int64_t)sb0 * Ops::BS + lane * 16;
+    int to_issue = my_rows;
+    auto issue_row = [&](uint32_t dst) {          // this warp's next row -> the stage at dst (an empty group past the end)
+        const int go = to_issue > 0;
+        if (FULL) {
+            cp_async16_if(go, 0, dst, src_next, pol);
+            cp_async16_if(go, 0, dst + 512, src_next + 512, pol);
+            cp_async16_if(go, 0, dst + 1024, src_next + 1024, pol);
+            cp_async16_if(go, 0, dst + 1536, src_next + 1536, pol);
+            cp_async16_if(go & lo16, 0, dst + 2048, src_next + 2048, pol);
+        } else {
+            const int have = go ? npc : 0;
+            cp_async16_if(have, 0, dst, src_next, pol);
+            cp_async16_if(have, 1, dst + 512, src_next + 512, pol);
+            cp_async16_if(have, 2, dst + 1024, src_next + 1024, pol);
+            cp_async16_if(have, 3, dst + 1536, src_next + 1536, pol);
+            cp_async16_if(have, 4, dst + 2048, src_next + 2048, pol);
         }
         cp_async_commit();
-        is_k++;
+        src_next += p.wstep;
+        to_issue--;
     };
-    // static weights: the first rows are requested while the previous kernel of the stream still runs.  Only p.early of
-    // the kStages rows: this SM's requests are served in order, and the other CTA of the SM (the PREVIOUS launch) is about
-    // to read its activations -- a deep burst here would sit in front of that latency-critical read.
+    // static weights: the first rows are requested while the previous kernel of the stream still runs (only p.early of the
+    // S stages: the other CTA of this SM -- the PREVIOUS launch -- is about to read its activations through the same
+    // load/store unit, and its requests queue behind these)
     const int early = p.pdl_prefetch ? p.early : 0;
-    for (int s = 0; s < early; s++) issue_row();
+#pragma unroll
+    for (int s = 0; s < S; s++)
+        if (s < early) issue_row(my_ring_s + s * stage_bytes);
     ggb_pdl_wait();
-    if (p.trace && tid == 0) p.trace[blockIdx.x * 4 + 1] = gtime();
+    if (tr && tid == 0) tr[1] = clk64();
 
     // ===================== q8_1-quantize X into shared memory (bit-identical to quantize_q8_1) =====================
+    // 4 lanes per 32-value group, U groups per thread and pass (U = 4 on long rows: the pass is a latency chain of loads,
+    // shuffles and a division, and every CTA repeats the whole row)
     const T *X = static_cast<const T *>(p.X);
     const int ngroups_row = p.K >> 5;
-    const int t4 = lane & 3;
     constexpr int GPI = (kNW * 32) / 4;
-    constexpr int U = 2;
-    for (int base = 0; base < ngroups_row; base += U * GPI) {
+    auto quantize_pass = [&](auto u_tag, int base, bool first) {
+        constexpr int U = decltype(u_tag)::value;
+        const int t4 = lane & 3;
         float v[U][8];
 #pragma unroll
         for (int u = 0; u < U; u++) {
@@ -205,8 +251,12 @@ mmvq_rg_kernel(const RgParams p) {
             }
         }
         // the rest of the weight pipeline goes out BEHIND the first activation loads
-        if (base == 0)
-            for (int s = early; s < kStages; s++) issue_row();
+        if (first) {
+#pragma unroll
+            for (int s = 0; s < S; s++)
+                if (s >= early) issue_row(my_ring_s + s * stage_bytes);
+            if (tr && tid == 0) tr[2] = clk64() + (long long)(v[0][0] == 123.456f);      // after the first X loads have landed
+        }
 #pragma unroll
         for (int u = 0; u < U; u++) {
             if (base + u * GPI >= ngroups_row) break;             // warp-uniform
@@ -227,7 +277,13 @@ mmvq_rg_kernel(const RgParams p) {
                 }
             }
         }
+    };
+    if (ngroups_row > 2 * GPI) {
+        for (int base = 0; base < ngroups_row; base += 4 * GPI) quantize_pass(std::integral_constant<int, 4>{}, base, base == 0);
+    } else {
+        for (int base = 0; base < ngroups_row; base += 2 * GPI) quantize_pass(std::integral_constant<int, 2>{}, base, base == 0);
     }
+    if (tr && tid == 0) tr[3] = clk64();
     __syncthreads();
 
     // this lane's item of every row chunk it will see: activations -> registers
@@ -245,23 +301,44 @@ mmvq_rg_kernel(const RgParams p) {
 #pragma unroll
         for (int i = 0; i < 32; i++) a[i] = 0u;
     }
-    if (p.trace && tid == 0) p.trace[blockIdx.x * 4 + 2] = gtime();
+    if (tr && tid == 0) tr[4] = clk64();
 
     // ===================== main loop: one step = chunk c of this warp's next row =====================
+    // Rows go four at a time (one reduction per four).  With S == 4 the stage of a row is its position in the group: all
+    // shared-memory offsets are constants.  Lanes without an item (partial chunks) read super-block 0 and their result is
+    // dropped: no branch around the dot products.
     const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
-    float part[4] = {0.f, 0.f, 0.f, 0.f};
+    const uint32_t hd0 = smem_u32(my_ring) + (live ? sbl : 0) * Ops::BS;  // the lane's super-block in stage 0
+    const int qoff = 16 + 64 * h;
+    // (opaque to the compiler: under the 80-register cap it would otherwise recompute these addresses from the thread
+    // index for every row, ~14 instructions)
+    uint32_t hd0_k = hd0, ring_k = my_ring_s;
+    asm volatile("" : "+r"(hd0_k), "+r"(ring_k));
+    uint32_t hdp = hd0_k;                                                // (S != 4: stage pointers advance and wrap)
+    uint32_t dstp = ring_k;
     int stage = 0;
+    float part[4] = {0.f, 0.f, 0.f, 0.f};
     for (int j0 = 0; j0 < my_rows; j0 += 4) {
 #pragma unroll
         for (int jj = 0; jj < 4; jj++) {
             part[jj] = 0.0f;
             if (j0 + jj < my_rows) {                                   // warp-uniform
-                cp_async_wait<kStages - 1>();                          // this thread's oldest row has landed
-                if (live && !(p.dbg & 2)) part[jj] = Ops::item(my_ring + (stage * kParts) * 32, a, d8, ds, h);
-                issue_row();                                           // refill the stage just consumed
-                if (++stage == kStages) stage = 0;
+                const uint32_t hp = (S == 4) ? hd0_k + jj * stage_bytes : hdp;
+                const uint32_t dp = (S == 4) ? ring_k + jj * stage_bytes : dstp;
+                cp_async_wait<S - 1>();                                // this thread's pieces of the oldest row have landed
+                __syncwarp();                                          // ... and so have the other lanes'
+                const float v = Ops::item(hp, hp + qoff, a, d8, ds, h);
+                part[jj] = (FULL || live) ? v : 0.0f;
+                __syncwarp();                                          // every lane has read the stage
+                issue_row(dp);                                         // refill it
+                if (S != 4) {
+                    hdp += stage_bytes;
+                    dstp += stage_bytes;
+                    if (++stage == S) { stage = 0; hdp = hd0_k; dstp = ring_k; }
+                }
             }
         }
+        if (tr && tid == 0 && j0 == 0) tr[5] = clk64();
         // four rows reduced together: xor 16 and xor 8 fold the four values onto the four lane octets, then 4, 2, 1.
         // Every row's sum is the same fixed tree whatever its position in the group (fp32 add is commutative).
         float x0 = (up16 ? part[2] : part[0]) + __shfl_xor_sync(0xffffffffu, up16 ? part[0] : part[2], 16);
@@ -286,7 +363,29 @@ mmvq_rg_kernel(const RgParams p) {
             ggb_yout_store<T>(p.yo, 0, r_begin + lr, s);
         }
     }
-    if (p.trace && tid == 0) p.trace[blockIdx.x * 4 + 3] = gtime();
+    if (tr && tid == 0) tr[6] = clk64();
+}
+
+template <int TYPE, typename T, int S, bool FULL>
+int launch_cfg(RgParams &p, int grid, int smem, cudaStream_t stream) {
+    const DeviceInfo &di = ggb_device_info();
+    static bool attr_set[64] = {};               // per instantiation and device; idempotent, so a race is harmless
+    if (!attr_set[di.dev]) {
+        GGB_CUDA_TRY(cudaFuncSetAttribute(mmvq_rg_kernel<TYPE, T, S, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin));
+        attr_set[di.dev] = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kNW * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmvq_rg_kernel<TYPE, T, S, FULL>, p));
+    return GGB_OK;
 }
 
 template <int TYPE, typename T>
@@ -303,15 +402,16 @@ int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, cudaStre
     p.nsb = (int)(K / 256);
     p.ipr = 2 * p.nsb;
     p.row_bytes = p.nsb * Ops::BS;
-    p.C = (p.ipr + kChunkItems - 1) / kChunkItems;
+    p.C = (p.nsb + 15) / 16;
     if (p.C > 4 || kNW % p.C != 0 || p.row_bytes % 16 != 0) return 1;
+    p.spc = (p.nsb + p.C - 1) / p.C;
     p.RW = kNW / p.C;
+    p.wstep = (long long)p.RW * p.row_bytes;
     p.x_vec = (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.xin.x2) & 15) == 0 &&
               (p.xin.ldx * (int64_t)sizeof(T)) % 16 == 0;
     p.pdl_prefetch = ggb_sb::g_pdl_prefetch;
     p.dbg = (ggb_sb::g_rg_mode >> 8) & 0xff;
     p.early = (ggb_sb::g_rg_mode >> 16) & 0xf;
-    if (p.early == 0 || p.early > kStages) p.early = 2;
     const int64_t max_ctas = (N + p.RW - 1) / p.RW;
     const int grid = (int)(max_ctas < di.sm_count ? max_ctas : di.sm_count);
     p.part_rows = p.C > 1 ? (int)((N + grid - 1) / grid + 1) : 0;
@@ -319,27 +419,18 @@ int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, cudaStre
     p.off_scales = ((int)K + 15) & ~15;
     p.off_part = p.off_scales + 2 * p.ipr * 16;
     p.off_slots = (p.off_part + p.part_rows * p.C * 4 + 127) & ~127;
-    const int smem = p.off_slots + kNW * kStages * kParts * 512;
-    if (smem > (di.max_smem_optin + 1024) / 2 - 1024) return 1;               // two CTAs per SM
+    const int half_sm = (di.max_smem_optin + 1024) / 2 - 1024;               // two CTAs per SM
+    const bool full = p.nsb % 16 == 0;
+    const int force_s = (ggb_sb::g_rg_mode >> 12) & 0xf;                     // debug: 3 or 4 stages
+    constexpr int stage_bytes = 16 * Ops::BS;
+    int S = (p.off_slots + kNW * 4 * stage_bytes <= half_sm) ? 4 : 3;
+    if (force_s == 3) S = 3;
+    const int smem = p.off_slots + kNW * S * stage_bytes;
+    if (smem > half_sm) return 1;
+    if (p.early == 0 || p.early > S) p.early = 1;
     p.trace = ggb_mmvq_trace_slot();
-
-    static bool attr_set[64] = {};               // per instantiation and device; idempotent, so a race is harmless
-    if (!attr_set[di.dev]) {
-        GGB_CUDA_TRY(cudaFuncSetAttribute(mmvq_rg_kernel<TYPE, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin));
-        attr_set[di.dev] = true;
-    }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kNW * 32);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmvq_rg_kernel<TYPE, T>, p));
-    return GGB_OK;
+    if (S == 4) return full ? launch_cfg<TYPE, T, 4, true>(p, grid, smem, stream) : launch_cfg<TYPE, T, 4, false>(p, grid, smem, stream);
+    return full ? launch_cfg<TYPE, T, 3, true>(p, grid, smem, stream) : launch_cfg<TYPE, T, 3, false>(p, grid, smem, stream);
 }
 
 template <int TYPE>

@@ -15,17 +15,17 @@ int g_l2_prefetch_mb = 0;    // L2 prefetch budget per launch in MB (0 = off: me
 using namespace ggb_sb;
 
 namespace {
-unsigned long long *g_trace = nullptr;   // debug: device buffer of 4 stamps per CTA per launch
+unsigned long long *g_trace = nullptr;   // debug: device buffer of 8 * 256 stamps per launch (ring kernel: 4 per CTA, rg kernel: 8)
 int g_trace_launch = 0;
 }  // namespace
 
-unsigned long long *ggb_mmvq_trace_slot() { return g_trace ? g_trace + (size_t)(g_trace_launch++) * 4 * 256 : nullptr; }
+unsigned long long *ggb_mmvq_trace_slot() { return g_trace ? g_trace + (size_t)(g_trace_launch++) * 8 * 256 : nullptr; }
 
 void ggb_mmvq_sb_set_static_weights(int on) { g_pdl_prefetch = on ? 1 : 0; }
 int ggb_mmvq_static_weights() { return g_pdl_prefetch; }
 int ggb_static_weights() { return g_pdl_prefetch; }
 int ggb_mmvq_l2_prefetch_mb() { return g_l2_prefetch_mb; }
-extern "C" void ggb_debug_mmvq_trace(void *device_buffer) {      // debug only: 4 * 256 u64 per launch, not in the header
+extern "C" void ggb_debug_mmvq_trace(void *device_buffer) {      // debug only: 8 * 256 u64 per launch
     g_trace = static_cast<unsigned long long *>(device_buffer);
     g_trace_launch = 0;
 }

@@ -25,7 +25,7 @@ if "tiled" in opt:    # largest TMA box of the generic kernel's tiled stages (0 
     _capi.lib.ggb_set_option(6, int(opt["tiled"]))
 l2 = int(opt.get("l2", "0"))
 _capi.lib.ggb_set_option(4, l2)
-_capi.lib.ggb_set_option(7, int(opt.get("rg", "0")))
+_capi.lib.ggb_set_option(7, int(opt.get("rg", "1")))
 shapes = ((14336, 4096), (4096, 14336), (28672, 8192), (8192, 28672))
 if "shapes" in opt:
     shapes = tuple(tuple(int(v) for v in sh.split("x")) for sh in opt["shapes"].split(","))

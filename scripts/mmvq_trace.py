@@ -11,7 +11,7 @@ N, K, t, B = int(opt.get("N", 14336)), int(opt.get("K", 4096)), int(opt.get("t",
 L = _capi.lib
 L.ggb_set_option(1, static); L.ggb_set_option(2, warps | (cap << 8))
 l2 = int(opt.get("l2", "0")); L.ggb_set_option(4, l2)
-L.ggb_set_option(7, int(opt.get("rg", "0")))
+L.ggb_set_option(7, int(opt.get("rg", "1")))
 L.ggb_debug_mmvq_trace.argtypes = [ctypes.c_void_p]
 dev = torch.device("cuda")
 base = torch.from_numpy(synth.random_blocks(t, N, K, seed=1)).to(dev)
@@ -30,7 +30,26 @@ with torch.cuda.stream(s):
     L.ggb_debug_mmvq_trace(None)
     for _ in range(3): g.replay()
     torch.cuda.synchronize()
-tr = trace.cpu().numpy().reshape(-1, 256, 4)[:nl, :148].astype(np.float64)
+raw = trace.cpu().numpy().reshape(-1, 2048)[:nl]
+rg = int(opt.get("rg", "1")) & 1
+if rg and B == 1 and t == 12:
+    # rg kernel: 8 stamps per CTA: clock64 at start, dep-wait done, first X loads landed, quantized, activations in registers,
+    # first 4 rows done, end; [7] = globaltimer at start
+    tr = raw.reshape(nl, 256, 8)[:, :148].astype(np.float64)
+    g0 = tr[0, :, 7].min()
+    print(f"rg={opt.get('rg')} static={static} N={N} K={K} B={B}: per-CTA phases in SM cycles (min / median / max over CTAs); start = globaltimer us")
+    names = ["start->dep-wait done", "->X loads landed", "->quantized", "->acts in regs", "->first 4 rows", "->end"]
+    for i in range(nl):
+        a = tr[i]
+        row = f"launch {i}: start {(a[:,7].min()-g0)/1e3:6.2f}..{(a[:,7].max()-g0)/1e3:6.2f} us |"
+        for k, nm in enumerate(names):
+            d = a[:, k + 1] - a[:, k]
+            row += f" {nm} {int(d.min())}/{int(np.median(d))}/{int(d.max())} |"
+        tot = a[:, 6] - a[:, 1]
+        row += f" dep-wait done->end {int(tot.min())}/{int(np.median(tot))}/{int(tot.max())}"
+        print(row)
+    sys.exit(0)
+tr = raw[:, :1024].reshape(nl, 256, 4)[:, :148].astype(np.float64)
 t0 = tr[0, :, 0].min()
 tr = (tr - t0) / 1e3
 print(f"l2={l2} static={static} warps={warps} cap={cap} N={N} K={K} B={B}   (us since first CTA start)")

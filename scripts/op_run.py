@@ -1,9 +1,14 @@
-"""Run one op a few times (for ncu captures and quick timings):  op_run.py {mmq|mmvq|dequant} type N K M [iters]"""
+"""Run one op a few times (for ncu captures and quick timings):  op_run.py {mmq|mmvq|dequant} type N K M [iters] [opt:<id>=<value> ...]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [os.path.join(ROOT, "ggml-libtorch_b200")]
 import torch, ggml
 from ggml import synth
+from ggml import _capi
+for a in [a for a in sys.argv if a.startswith("opt:")]:          # opt:<ggb_option id>=<value>
+    k, v = a[4:].split("=")
+    _capi.lib.ggb_set_option(int(k), int(v))
+sys.argv = [a for a in sys.argv if not a.startswith("opt:")]
 op, t, N, K, M = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5])
 iters = int(sys.argv[6]) if len(sys.argv) > 6 else 5
 w = torch.from_numpy(synth.random_blocks(t, N, K, seed=1)).cuda()

@@ -80,6 +80,62 @@ __global__ void ldg_kernel(const uint4 *src, size_t n16, unsigned *sink) {
     if (acc == 0x12345u) sink[0] = acc;
 }
 
+
+// per-warp LDGSTS (cp.async.cg 16 B per lane, coalesced) rings: warp w streams chunks w, w + NW, ... of its CTA's contiguous
+// range; DEPTH chunks in flight per warp; optionally the chunk `l2_ahead` steps further is pulled into L2 (prefetch.global.L2)
+template <int DEPTH>
+__global__ void ldgsts_ring_kernel(const uint8_t *src, size_t total, int chunk_bytes, int l2_ahead, unsigned *sink) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int nw = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t per_cta = total / gridDim.x / chunk_bytes * chunk_bytes;
+    const uint8_t *base = src + (size_t)blockIdx.x * per_cta;
+    const int nchunks = (int)(per_cta / chunk_bytes);
+    const int mine = (nchunks - warp + nw - 1) / nw;
+    const int n16 = chunk_bytes / 16;
+    const uint32_t ring = smem_u32(smem) + warp * DEPTH * chunk_bytes + lane * 16;
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    int issued = 0;
+    auto issue = [&]() {
+        if (issued < mine) {
+            const uint8_t *g = base + (size_t)(warp + (size_t)issued * nw) * chunk_bytes + lane * 16;
+            const uint32_t d = ring + (issued % DEPTH) * chunk_bytes;
+            for (int q = 0; lane + 32 * q < n16; q++)
+                asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d + 512 * q), "l"(g + 512 * q), "l"(pol) : "memory");
+            if (l2_ahead > 0 && issued + l2_ahead < mine && lane * 128 < chunk_bytes)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)(warp + (size_t)(issued + l2_ahead) * nw) * chunk_bytes + lane * 128));
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        issued++;
+    };
+    for (int s = 0; s < DEPTH; s++) issue();
+    unsigned acc = 0;
+    for (int k = 0; k < mine; k++) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH - 1) : "memory");
+        __syncwarp();
+        acc ^= *reinterpret_cast<const unsigned *>(smem + (size_t)(warp * DEPTH + k % DEPTH) * chunk_bytes + (lane * 16) % chunk_bytes);
+        __syncwarp();
+        issue();
+    }
+    if (acc == 0x12345u) sink[0] = acc;
+}
+
+// plain coalesced LDG.128 stream with a bounded number of loads in flight per thread (bandwidth vs bytes in flight)
+template <int UNR>
+__global__ void ldg_bounded_kernel(const uint4 *src, size_t n16, unsigned *sink) {
+    const size_t per_cta = n16 / gridDim.x;
+    const uint4 *p = src + (size_t)blockIdx.x * per_cta;
+    unsigned acc = 0;
+    for (size_t i = threadIdx.x; i + (size_t)(UNR - 1) * blockDim.x < per_cta; i += (size_t)UNR * blockDim.x) {
+        uint4 v[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; u++) v[u] = __ldcs(p + i + (size_t)u * blockDim.x);
+#pragma unroll
+        for (int u = 0; u < UNR; u++) acc ^= v[u].x ^ v[u].y ^ v[u].z ^ v[u].w;
+    }
+    if (acc == 0x12345u) sink[0] = acc;
+}
+
 int main() {
     int sms = 0;
     CK(cudaSetDevice(0));
@@ -135,6 +191,47 @@ int main() {
                        first ? "" : ",\n", cps, nw, sb, depth, cps * nw * depth * sb / 1024, g);
                 first = false;
             }
+
+    printf("\n ],\n \"ldgsts_ring\": [\n");
+    {
+        bool f2 = true;
+        auto one = [&](auto kern, int depth, int cps, int nw, int cb, int l2a) {
+            const int smem = nw * depth * cb;
+            if (smem > (cps == 1 ? 220 : 110) * 1024) return;
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            const double g = run([&] { kern<<<sms * cps, nw * 32, smem>>>(buf, total, cb, l2a, sink); });
+            printf("%s  {\"ctas_per_sm\": %d, \"warps\": %d, \"chunk_bytes\": %d, \"depth\": %d, \"l2_ahead\": %d, \"in_flight_KB_per_sm\": %d, \"GBps\": %.0f}",
+                   f2 ? "" : ",\n", cps, nw, cb, depth, l2a, cps * smem / 1024, g);
+            f2 = false;
+        };
+        for (int cps : {1, 2})
+            for (int nw : {8, 12, 16})
+                for (int cb : {2304, 4608})
+                    for (int l2a : {0, 4, 12}) {
+                        one(ldgsts_ring_kernel<2>, 2, cps, nw, cb, l2a);
+                        one(ldgsts_ring_kernel<3>, 3, cps, nw, cb, l2a);
+                        one(ldgsts_ring_kernel<4>, 4, cps, nw, cb, l2a);
+                        one(ldgsts_ring_kernel<6>, 6, cps, nw, cb, l2a);
+                        one(ldgsts_ring_kernel<8>, 8, cps, nw, cb, l2a);
+                    }
+    }
+    printf("\n ],\n \"ldg_bounded\": [\n");
+    {
+        bool f3 = true;
+        auto one = [&](auto kern, int unr, int cps, int thr) {
+            const double g = run([&] { kern<<<sms * cps, thr>>>((const uint4 *)buf, total / 16, sink); });
+            printf("%s  {\"ctas_per_sm\": %d, \"threads\": %d, \"unroll\": %d, \"in_flight_KB_per_sm\": %d, \"GBps\": %.0f}", f3 ? "" : ",\n", cps, thr, unr,
+                   cps * thr * unr * 16 / 1024, g);
+            f3 = false;
+        };
+        for (int cps : {1, 2})
+            for (int thr : {256, 384, 512}) {
+                one(ldg_bounded_kernel<2>, 2, cps, thr);
+                one(ldg_bounded_kernel<4>, 4, cps, thr);
+                one(ldg_bounded_kernel<8>, 8, cps, thr);
+                one(ldg_bounded_kernel<16>, 16, cps, thr);
+            }
+    }
     printf("\n ]}\n");
     return 0;
 }
