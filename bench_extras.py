@@ -14,6 +14,10 @@ import statistics
 import torch
 
 NOMINAL_INT8_TOPS = 4500.0      # dense int8 tcgen05 peak of a B200 (2x the bf16 nominal of 2250)
+# measured on this pool (scripts/probes/i8_probe.cu, profiles/r02_i8_probe.json): a bare tcgen05.mma.kind::i8 issue loop,
+# M = 128 x N = 256 x K = 32 per instruction, 148 SMs, operands resident in shared memory
+MEASURED_INT8_TOPS = 4416.6
+MEASURED_F16_ISSUE_TFLOPS = 2100.3
 
 
 def _time_graph(fn, iters: int, warm: int = 3) -> float:
@@ -78,7 +82,11 @@ def mmvq_section(ggml, synth, dev, peaks, peak_kind):
 
 def mmq_section(ggml, synth, dev, peaks, peak_kind):
     out = {"unit": "TOPS (2*M*N*K / time)", "peak": NOMINAL_INT8_TOPS,
-           "peak_source": "nominal dense int8 (no measured int8 peak in MEASURED_PEAKS.json)",
+           "peak_source": "nominal dense int8; measured bare kind::i8 issue loop on this pool: 4416.6 TOPS (profiles/r02_i8_probe.json)",
+           "int8_measured_issue_loop_tops": MEASURED_INT8_TOPS, "f16_measured_issue_loop_tflops": MEASURED_F16_ISSUE_TFLOPS,
+           "exact_q8_1_int8_ceiling_tops": 417.6,
+           "exact_q8_1_int8_ceiling_note": "kind::i8 128x256x32 tiles with the per-32 TMEM drain + fp32 rescale that exact q8_1 semantics "
+                                           "need (8 drain warps, double-buffered accumulators), measured: 264-418 TOPS -- below this kernel",
            "bf16_measured_tflops": peaks.get("bf16_tflops"),
            "method": "CUDA events around 10 launches after 3 warm-ups, fp16 x/y, workspace preallocated", "cases": []}
     launches = 0
@@ -103,14 +111,17 @@ def mmq_section(ggml, synth, dev, peaks, peak_kind):
             launches += iters + 3
             tops = 2.0 * M * N * K / (ms * 1e-3) / 1e12
             out["cases"].append({"type": tname, "M": M, "N": N, "K": K, "ms": ms, "TOPS": tops,
-                                 "frac_of_int8_peak": tops / NOMINAL_INT8_TOPS})
+                                 "frac_of_int8_peak": tops / NOMINAL_INT8_TOPS,
+                                 "frac_of_measured_bf16_peak": tops / float(peaks.get("bf16_tflops", 1595.8))})
     return out, launches
 
 
 def tp_mlp_section(ggml, synth, dev, rank, world, peaks, peak_kind):
-    """BASELINE configs[4]: Llama-3-70B MLP (hidden 8192, intermediate 28672), Q4_K gate/up and Q6_K down,
-    column-parallel over `world` ranks with one NCCL all-gather per projection.  Device time (CUDA events),
-    max over ranks.  Weight GB/s counts every rank's shard bytes (the whole layer) per step."""
+    """BASELINE configs[4], one block, all exchange variants and batch sizes (the headline of bench.py is the 80-block stack
+    at batch 1 on the fused path): Llama-3-70B MLP (hidden 8192, intermediate 28672), Q4_K gate/up and Q6_K down,
+    column-parallel over `world` ranks.  Device time (CUDA events), max over ranks.  Weight GB/s counts every rank's shard
+    bytes (the whole layer) per step.  NOTE: one block is 457 MB / tp per rank -- below the L2 size for tp >= 4, so the
+    replayed block is partly L2-resident there; the headline stack is not."""
     import torch.distributed as dist
     from ggml.parallel import ColumnParallelQuantLinear, QuantMLP
     H, I = 8192, 28672
@@ -142,7 +153,7 @@ def tp_mlp_section(ggml, synth, dev, rank, world, peaks, peak_kind):
     launches = 0
     for name, fused in variants:
       mlp = mlps[name]
-      for M in ((1, 8) if fused else (1, 8, 512)):
+      for M in ((1, 8) if fused else (1, 8, 512, 4096)):
         x = torch.randn(M, H, dtype=torch.float16, device=dev)
         reps = 8 if M <= 8 else 2
         how = "cuda-graph replay"
@@ -213,6 +224,44 @@ def config0_section(ggml, synth, dev, peaks, peak_kind):
     return out, launches
 
 
+def dequant_sweep_section(ggml, synth, dev, peaks, peak_kind):
+    """BASELINE configs[1] (round 1's headline): the K-quant dequantize sweep Q2_K..Q6_K of 4096x14336 -> fp16, back-to-back
+    launches (5 per pass: 166 MB of blocks in, 587 MB out -- 6x the L2), algorithmic GB/s = blocks read + fp16 written."""
+    hbm = float(peaks["hbm_gbs"])
+    rows, cols = 4096, 14336
+    sweep = (10, 11, 12, 13, 14)
+    w = {t: torch.from_numpy(synth.random_blocks(t, rows, cols, seed=t)).to(dev) for t in sweep}
+    o = {t: torch.empty((rows, cols), dtype=torch.float16, device=dev) for t in sweep}
+    step_bytes = sum(x.numel() for x in w.values()) + rows * cols * 2 * len(sweep)
+
+    def step():
+        for t in sweep:
+            ggml.dequantize_out(w[t], t, rows, cols, o[t])
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 20
+    a.record()
+    for _ in range(reps):
+        step()
+    b.record()
+    b.synchronize()
+    ms = a.elapsed_time(b) / reps
+    per = {}
+    for t in sweep:
+        a.record()
+        for _ in range(10):
+            ggml.dequantize_out(w[t], t, rows, cols, o[t])
+        b.record()
+        b.synchronize()
+        per[synth.NAMES[t]] = (w[t].numel() + rows * cols * 2) / (a.elapsed_time(b) / 10 * 1e-3) / 1e9
+    gbs = step_bytes / (ms * 1e-3) / 1e9
+    return {"unit": "GB/s (block bytes + fp16 output bytes)", "sweep_GBps": gbs, "frac_of_hbm_peak": gbs / hbm, "ms_per_sweep": ms,
+            "per_type_GBps_same_type_back_to_back": per}, 5 * (reps + 3) + 50
+
+
 def all_types_section(ggml, synth, dev, peaks, peak_kind):
     """Every type the library serves, on one shape each: dequantize 4096x14336 -> fp16 (algorithmic bytes = blocks read +
     fp16 written) and MMVQ 14336x4096 at batch 1 and 8 (weight bytes / time).  The headline sweep and the MMVQ section
@@ -275,8 +324,8 @@ def run(ggml, synth, dev, rank, world, peaks, peak_kind):
         if rank == 0:
             extras["tp_mlp"] = {"error": f"{type(e).__name__}: {e}"}
     if rank == 0:
-        for name, fn in (("config0_gpu", config0_section), ("mmvq", mmvq_section), ("mmq", mmq_section),
-                         ("all_types", all_types_section)):
+        for name, fn in (("config0_gpu", config0_section), ("dequant_sweep", dequant_sweep_section), ("mmvq", mmvq_section),
+                         ("mmq", mmq_section), ("all_types", all_types_section)):
             try:
                 extras[name], k = fn(ggml, synth, dev, peaks, peak_kind)
                 n += k

@@ -27,7 +27,8 @@ void ggb_mmvq_rg_set_mode(int mode);
 int ggb_mmvq_mma_impl(const void *W, const void *X, void *Y, int type, int xy_dtype, int64_t B, int64_t K, int64_t N,
                       void *ws, int64_t ws_bytes, cudaStream_t stream);
 int ggb_mmvq_sb_impl(const void *W, const void *X, void *Y, int type, int xy_dtype, int64_t B, int64_t K, int64_t N,
-                     cudaStream_t stream);
+                     void *ws, int64_t ws_bytes, cudaStream_t stream);
+void ggb_mmvq_sb_set_prequant_min_k(int k);
 
 // ---------------------------------------------------------------- errors
 static thread_local char g_err[512] = "";
@@ -129,6 +130,9 @@ int ggb_set_option(int option, int value) {
             return GGB_OK;
         case GGB_OPT_MMVQ_RG:
             ggb_mmvq_rg_set_mode(value);
+            return GGB_OK;
+        case GGB_OPT_MMVQ_PREQUANT:
+            ggb_mmvq_sb_set_prequant_min_k(value);
             return GGB_OK;
         default:
             ggb_set_error("ggb_set_option: unknown option %d", option);
@@ -258,7 +262,7 @@ int ggb_mmvq_fused(const void *W, const void *X, const void *X2, int64_t ldx, in
     g_xin = &x;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int rc = ggb_mmvq_mma_impl(W, X, nullptr, type, xy_dtype, B, K, N, ws, ws_bytes, st);
-    if (rc == 1) rc = ggb_mmvq_sb_impl(W, X, nullptr, type, xy_dtype, B, K, N, st);
+    if (rc == 1) rc = ggb_mmvq_sb_impl(W, X, nullptr, type, xy_dtype, B, K, N, ws, ws_bytes, st);
     g_yout = nullptr;
     g_xin = nullptr;
     if (rc == 1) {

@@ -567,11 +567,15 @@ int ggb_mmvq_mma_impl(const void *W, const void *X, void *Y, int type, int xy_dt
                       void *ws, int64_t ws_bytes, cudaStream_t stream);
 int64_t ggb_mmvq_mma_workspace_bytes(int type, int64_t B, int64_t K);
 
-int64_t ggb_mmvq_workspace_bytes_impl(int type, int64_t B, int64_t K, int64_t) { return ggb_mmvq_mma_workspace_bytes(type, B, K); }
+int64_t ggb_mmvq_sb_workspace_bytes(int type, int64_t B, int64_t K);
+int64_t ggb_mmvq_workspace_bytes_impl(int type, int64_t B, int64_t K, int64_t) {
+    const int64_t a = ggb_mmvq_mma_workspace_bytes(type, B, K), b = ggb_mmvq_sb_workspace_bytes(type, B, K);
+    return a > b ? a : b;
+}
 
 // mmvq_sb.cu: the super-block-per-lane fast path (returns 1 when it does not apply)
 int ggb_mmvq_sb_impl(const void *W, const void *X, void *Y, int type, int xy_dtype, int64_t B, int64_t K, int64_t N,
-                     cudaStream_t stream);
+                     void *ws, int64_t ws_bytes, cudaStream_t stream);
 
 int ggb_mmvq_impl(const void *W, const void *X, void *Y, int type, int xy_dtype, int64_t B, int64_t K, int64_t N,
                   void *ws, int64_t ws_bytes, cudaStream_t stream) {
@@ -584,7 +588,7 @@ int ggb_mmvq_impl(const void *W, const void *X, void *Y, int type, int xy_dtype,
         if (rc != 1) return rc;
     }
     {
-        const int rc = ggb_mmvq_sb_impl(W, X, Y, type, xy_dtype, B, K, N, stream);
+        const int rc = ggb_mmvq_sb_impl(W, X, Y, type, xy_dtype, B, K, N, ws, ws_bytes, stream);
         if (rc != 1) return rc;
     }
     switch (type) {

@@ -48,6 +48,8 @@ struct RgParams {
     int spc;             // super-blocks per chunk
     int early;           // rows per warp requested before the dependency wait (static weights), 1..kStages
     long long wstep;     // bytes between two consecutive rows of a warp = RW * row_bytes
+    const uint8_t *image; // != nullptr: the q8_1 activation image written by the previous launch (mmvq_sb_prequant_kernel,
+                          // [8][ipr] quants at 0, [2][ipr] scale table at off_scales): every lane loads ITS item from it
     int part_rows;       // rows the partial-sum area holds (C > 1)
     int x_vec;
     int pdl_prefetch;
@@ -278,6 +280,29 @@ mmvq_rg_kernel(const RgParams p) {
             }
         }
     };
+    uint32_t a[32];
+    float4 d8 = make_float4(0.f, 0.f, 0.f, 0.f), ds = d8;
+    if (p.image != nullptr) {
+        // pre-quantized: no shared-memory staging, no CTA barrier -- 10 x 16 bytes per lane straight from L2
+#pragma unroll
+        for (int s = 0; s < S; s++)
+            if (s >= early) issue_row(my_ring_s + s * stage_bytes);
+        const uint4 *iq = reinterpret_cast<const uint4 *>(p.image);
+        const float4 *is = reinterpret_cast<const float4 *>(p.image + p.off_scales);
+        if (live) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const uint4 v = __ldg(iq + i * ipr + item);
+                a[4 * i] = v.x; a[4 * i + 1] = v.y; a[4 * i + 2] = v.z; a[4 * i + 3] = v.w;
+            }
+            d8 = __ldg(is + item);
+            ds = __ldg(is + ipr + item);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; i++) a[i] = 0u;
+        }
+        if (tr && tid == 0) { tr[2] = clk64(); tr[3] = tr[2]; }
+    } else {
     if (ngroups_row > 2 * GPI) {
         for (int base = 0; base < ngroups_row; base += 4 * GPI) quantize_pass(std::integral_constant<int, 4>{}, base, base == 0);
     } else {
@@ -287,8 +312,6 @@ mmvq_rg_kernel(const RgParams p) {
     __syncthreads();
 
     // this lane's item of every row chunk it will see: activations -> registers
-    uint32_t a[32];
-    float4 d8 = make_float4(0.f, 0.f, 0.f, 0.f), ds = d8;
     if (live) {
 #pragma unroll
         for (int i = 0; i < 8; i++) {
@@ -300,6 +323,7 @@ mmvq_rg_kernel(const RgParams p) {
     } else {
 #pragma unroll
         for (int i = 0; i < 32; i++) a[i] = 0u;
+    }
     }
     if (tr && tid == 0) tr[4] = clk64();
 
@@ -389,10 +413,11 @@ int launch_cfg(RgParams &p, int grid, int smem, cudaStream_t stream) {
 }
 
 template <int TYPE, typename T>
-int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, cudaStream_t stream) {
+int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, const void *image, int probe_only, cudaStream_t stream) {
     using Ops = RgOps<TYPE>;
     const DeviceInfo &di = ggb_device_info();
     RgParams p;
+    p.image = static_cast<const uint8_t *>(image);
     p.W = static_cast<const uint8_t *>(W);
     p.X = X;
     p.yo = ggb_make_yout(Y, N);
@@ -427,6 +452,7 @@ int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, cudaStre
     if (force_s == 3) S = 3;
     const int smem = p.off_slots + kNW * S * stage_bytes;
     if (smem > half_sm) return 1;
+    if (probe_only) return 2;
     if (p.early == 0 || p.early > S) p.early = 1;
     p.trace = ggb_mmvq_trace_slot();
     if (S == 4) return full ? launch_cfg<TYPE, T, 4, true>(p, grid, smem, stream) : launch_cfg<TYPE, T, 4, false>(p, grid, smem, stream);
@@ -434,11 +460,12 @@ int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, cudaStre
 }
 
 template <int TYPE>
-int dispatch_dtype(const void *W, const void *X, void *Y, int dt, int64_t K, int64_t N, cudaStream_t stream) {
+int dispatch_dtype(const void *W, const void *X, void *Y, int dt, int64_t K, int64_t N, const void *image, int probe_only,
+                   cudaStream_t stream) {
     switch (dt) {
-        case GGB_F32:  return launch<TYPE, float>(W, X, Y, K, N, stream);
-        case GGB_F16:  return launch<TYPE, __half>(W, X, Y, K, N, stream);
-        case GGB_BF16: return launch<TYPE, __nv_bfloat16>(W, X, Y, K, N, stream);
+        case GGB_F32:  return launch<TYPE, float>(W, X, Y, K, N, image, probe_only, stream);
+        case GGB_F16:  return launch<TYPE, __half>(W, X, Y, K, N, image, probe_only, stream);
+        case GGB_BF16: return launch<TYPE, __nv_bfloat16>(W, X, Y, K, N, image, probe_only, stream);
         default: return 1;
     }
 }
@@ -447,12 +474,13 @@ int dispatch_dtype(const void *W, const void *X, void *Y, int dt, int64_t K, int
 
 void ggb_mmvq_rg_set_mode(int mode) { ggb_sb::g_rg_mode = mode; }
 
-// returns GGB_OK / a negative status, or 1 when this kernel does not apply (the caller goes on to mmvq_sb / mmvq)
+// returns GGB_OK / a negative status, or 1 when this kernel does not apply (the caller goes on to mmvq_sb / mmvq);
+// probe_only: 2 = it applies (nothing launched)
 int ggb_mmvq_rg_impl(const void *W, const void *X, void *Y, int type, int xy_dtype, int64_t B, int64_t K, int64_t N,
-                     cudaStream_t stream) {
+                     const void *image, int probe_only, cudaStream_t stream) {
     if (!(ggb_sb::g_rg_mode & 1) || B != 1 || K % 256 != 0 || K > 16384 || (reinterpret_cast<uintptr_t>(W) & 15)) return 1;
     switch (type) {
-        case T_Q4_K: return dispatch_dtype<T_Q4_K>(W, X, Y, xy_dtype, K, N, stream);
+        case T_Q4_K: return dispatch_dtype<T_Q4_K>(W, X, Y, xy_dtype, K, N, image, probe_only, stream);
         default: return 1;
     }
 }

@@ -58,6 +58,8 @@ struct SbParams {
     int pdl_prefetch;    // 1: weights are static, the producer does not wait for the previous kernel
     int l2_prefetch;     // bytes of this CTA's weight range to pull into L2 while waiting for the previous kernel
     int staged;          // long rows, B <= 2: quantize the activations K-chunk by K-chunk around the first row group's slots
+    const uint8_t *image; // != nullptr: the q8_1 activation image (this kernel's shared-memory bytes [0, image_bytes), written by
+    int image_bytes;      //             mmvq_sb_prequant_kernel, the previous launch of the stream) is copied in instead of quantizing
     unsigned long long *trace;   // debug: per-CTA globaltimer stamps {start, after dependency wait, first slot, end}
 };
 
@@ -475,6 +477,57 @@ __device__ __forceinline__ void run_batches(const uint8_t *w0, const uint8_t *w1
     }
 }
 
+// quantize + store 32-value group `gi` of the range [g_lo, g_lo + span) x B: x = this lane's 8 values (lane t4 of the quad)
+template <int TYPE, int B>
+__device__ __forceinline__ void sb_q_store1(uint4 *act_q, float4 *act_s, int ipr, float (&x)[8], int gi, int g_lo, int span, int t4) {
+    using Ops = SbOps<TYPE>;
+    const bool live = gi < B * span;
+    const int b = (live && B > 1) ? gi / span : 0;
+    const int g = live ? g_lo + gi - b * span : 0;
+    const Q8Group q = q8_1_quantize_group<Ops::NEED_S8>(x);
+    int mine = __dp4a((int)q.q_lo, 0x01010101, __dp4a((int)q.q_hi, 0x01010101, 0));
+    mine += __shfl_xor_sync(0xffffffffu, mine, 1);                 // sum of this 16-value half
+    const int other = __shfl_xor_sync(0xffffffffu, mine, 2);
+    if (live) {
+        const int it = g >> 2, j = g & 3;                          // item, group inside the item
+        const int i = 2 * j + (t4 >> 1);                           // 16-value chunk inside the item
+        uint8_t *dst = reinterpret_cast<uint8_t *>(act_q + (b * 8 + i) * ipr + it) + 8 * (t4 & 1);
+        *reinterpret_cast<uint2 *>(dst) = make_uint2(q.q_lo, q.q_hi);
+        if (t4 == 0)
+            Ops::store_scales(act_s + (b * Ops::SCF4) * ipr + it, ipr, j, __half2float(__float2half_rn(q.d)), mine, other,
+                              __half2float(__float2half_rn(q.sum)));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The activation image as its own (tiny) launch: long rows, and the fused SwiGLU down projection, whose activation
+// quantization would otherwise be repeated by all 148 CTAs of the GEMV (K = 28672 with SwiGLU: ~25 us of a 67 us kernel).
+// One quad per 32-value group, 64 groups per CTA; the image is byte for byte what mmvq_sb_kernel / mmvq_rg_kernel keep in
+// shared memory ([B][8][ipr] quants | [B][SCF4][ipr] scale table), so the GEMV's prologue becomes one coalesced copy.
+// Programmatic dependent launch on both sides: the GEMV's CTAs are resident (and stream weights) while this runs.
+// ------------------------------------------------------------------------------------------------
+template <int TYPE, int B, typename T>
+__global__ void __launch_bounds__(256)
+mmvq_sb_prequant_kernel(const void *Xv, const GgbXIn xin, const int K, const int x_vec, uint8_t *image, const int off_scales) {
+    pdl_launch_dependents();
+    pdl_wait();
+    uint4 *act_q = reinterpret_cast<uint4 *>(image);
+    float4 *act_s = reinterpret_cast<float4 *>(image + off_scales);
+    const T *X = static_cast<const T *>(Xv);
+    const int ipr = K >> 7, span = K >> 5, total = B * span;
+    const int t4 = threadIdx.x & 3;
+    const int gi = blockIdx.x * 64 + (threadIdx.x >> 2);
+    float v[8];
+    if (gi < total) {
+        const int b = (B == 1) ? 0 : gi / span, g = gi - b * span;
+        load_act8<T>(X, static_cast<const T *>(xin.x2), xin.ldx, b, g * 32 + t4 * 8, x_vec != 0, v);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = 0.0f;
+    }
+    sb_q_store1<TYPE, B>(act_q, act_s, ipr, v, gi, 0, span, t4);
+}
+
 // ------------------------------------------------------------------------------------------------
 // the kernel: NW warps, all consumers; every warp streams its own slots (no producer warp, no round trip
 // through another thread when a slot is recycled).  NW = 8 with <= 113 KB of shared memory lets TWO CTAs
@@ -567,25 +620,7 @@ mmvq_sb_kernel(const SbParams p, const int g_defer) {
     const int t4 = lane & 3;
     constexpr int GPI = (NW * 32) / 4;                        // groups per pass of the CTA
     constexpr int U = (B <= 2) ? 4 : 2;                       // passes in flight (independent loads, interleaved math)
-    // quantize + store the group `gi` of the range [g_lo, g_lo + span) x B this thread's quad owns in pass u
-    auto q_store1 = [&](float (&x)[8], int gi, int g_lo, int span) {
-        const bool live = gi < B * span;
-        const int b = (live && B > 1) ? gi / span : 0;
-        const int g = live ? g_lo + gi - b * span : 0;
-        const Q8Group q = q8_1_quantize_group<Ops::NEED_S8>(x);
-        int mine = __dp4a((int)q.q_lo, 0x01010101, __dp4a((int)q.q_hi, 0x01010101, 0));
-        mine += __shfl_xor_sync(0xffffffffu, mine, 1);                 // sum of this 16-value half
-        const int other = __shfl_xor_sync(0xffffffffu, mine, 2);
-        if (live) {
-            const int it = g >> 2, j = g & 3;                          // item, group inside the item
-            const int i = 2 * j + (t4 >> 1);                           // 16-value chunk inside the item
-            uint8_t *dst = reinterpret_cast<uint8_t *>(act_q + (b * 8 + i) * ipr + it) + 8 * (t4 & 1);
-            *reinterpret_cast<uint2 *>(dst) = make_uint2(q.q_lo, q.q_hi);
-            if (t4 == 0)
-                Ops::store_scales(act_s + (b * Ops::SCF4) * ipr + it, ipr, j, __half2float(__float2half_rn(q.d)), mine, other,
-                                  __half2float(__float2half_rn(q.sum)));
-        }
-    };
+    auto q_store1 = [&](float (&x)[8], int gi, int g_lo, int span) { sb_q_store1<TYPE, B>(act_q, act_s, ipr, x, gi, g_lo, span, t4); };
     auto quantize_range = [&](int g_lo, int g_hi) {
         const int span = g_hi - g_lo, total = B * span;
         for (int base = 0; base < total; base += U * GPI) {
@@ -613,7 +648,14 @@ mmvq_sb_kernel(const SbParams p, const int g_defer) {
     // of 3.3 us of quantization (K = 14336) sit in front of the weight stream.
     constexpr int kChunkGroups = 128;
     const bool staged = p.staged != 0;
-    quantize_range(0, staged ? min(kChunkGroups, ngroups_row) : ngroups_row);
+    if (p.image != nullptr) {
+        // the image was written by the previous launch (mmvq_sb_prequant_kernel): one coalesced copy, L2 hits
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.image);
+        uint4 *dst = reinterpret_cast<uint4 *>(smem);
+        for (int i = tid; i < (p.image_bytes >> 4); i += NW * 32) dst[i] = src[i];
+    } else {
+        quantize_range(0, staged ? min(kChunkGroups, ngroups_row) : ngroups_row);
+    }
     __syncthreads();
     if (p.trace && tid == 0) p.trace[blockIdx.x * 4 + 2] = gtime();
 
@@ -790,15 +832,42 @@ mmvq_sb_kernel(const SbParams p, const int g_defer) {
 
 // tuning state shared by the per-type translation units (defined once in mmvq_sb.cu)
 namespace ggb_sb {
-extern int g_pdl_prefetch, g_force_warps, g_smem_cap_kb, g_staged, g_defer_reduce, g_l2_prefetch_mb;
+extern int g_pdl_prefetch, g_force_warps, g_smem_cap_kb, g_staged, g_defer_reduce, g_l2_prefetch_mb, g_prequant_min_k;
 }
 unsigned long long *ggb_mmvq_trace_slot();
 
 namespace {
 using namespace ggb_sb;
 
+// bytes of the activation image of (TYPE, B, K) = the kernels' shared-memory prefix
+template <int TYPE>
+int64_t sb_image_bytes(int64_t B, int64_t K) {
+    return ((B * K + 15) & ~(int64_t)15) + B * SbOps<TYPE>::SCF4 * (K / 128) * 16;
+}
+
+template <int TYPE, int B, typename T>
+int launch_prequant(const void *X, int64_t K, void *image, cudaStream_t stream) {
+    const GgbXIn xin = ggb_make_xin(K);
+    const int x_vec = (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(xin.x2) & 15) == 0 &&
+                      (xin.ldx * (int64_t)sizeof(T)) % 16 == 0;
+    const int groups = (int)(B * (K / 32));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((groups + 63) / 64);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmvq_sb_prequant_kernel<TYPE, B, T>, X, xin, (int)K, x_vec, static_cast<uint8_t *>(image),
+                                    (int)((B * K + 15) & ~(int64_t)15)));
+    return GGB_OK;
+}
+
 template <int TYPE, int B, typename T, int NW>
-int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, cudaStream_t stream) {
+int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, const void *image, cudaStream_t stream) {
     using Ops = SbOps<TYPE>;
     constexpr int kThreads = NW * 32;
     const DeviceInfo &di = ggb_device_info();
@@ -828,7 +897,10 @@ int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, cudaStre
               (p.xin.ldx * (int64_t)sizeof(T)) % 16 == 0;
     // measured (same box, vs quantizing everything up front): Q4_K +3.4 % at K = 14336 and 28672, Q6_K +2.3 % at 14336 but
     // -7.7 % at 28672 (six CTA-wide barriers around heavier slots)
-    p.staged = (p.nchunks > 1 && (TYPE != T_Q6_K || p.nchunks <= 4) && B <= 2 && g_staged && p.x_vec && p.xin.x2 == nullptr) ? 1 : 0;
+    p.image = static_cast<const uint8_t *>(image);
+    p.image_bytes = (int)sb_image_bytes<TYPE>(B, K);
+    p.staged = (image == nullptr && p.nchunks > 1 && (TYPE != T_Q6_K || p.nchunks <= 4) && B <= 2 && g_staged && p.x_vec &&
+                p.xin.x2 == nullptr) ? 1 : 0;
     p.pdl_prefetch = g_pdl_prefetch;
     p.trace = ggb_mmvq_trace_slot();
     const int act_q = (int)(B * K);
@@ -870,32 +942,44 @@ int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, cudaStre
 }
 
 template <int TYPE, int B, typename T>
-int launch_nw(const void *W, const void *X, void *Y, int64_t K, int64_t N, cudaStream_t stream) {
+int launch_nw(const void *W, const void *X, void *Y, int64_t K, int64_t N, void *ws, int64_t ws_bytes, cudaStream_t stream) {
+    // B <= 2: the activation image as its own launch when the caller's workspace holds it and the row is long or the
+    // activation is a fused SwiGLU (ggb_mmvq_workspace_bytes asks for it); the GEMV then copies it instead of quantizing
+    const void *image = nullptr;
+    if constexpr (B <= 2) {
+        const GgbXIn xin = ggb_make_xin(K);
+        if (ws != nullptr && ws_bytes >= sb_image_bytes<TYPE>(B, K) && (reinterpret_cast<uintptr_t>(ws) & 15) == 0 &&
+            g_prequant_min_k > 0 && (K >= g_prequant_min_k || (xin.x2 != nullptr && K >= 4096))) {
+            const int rc = launch_prequant<TYPE, B, T>(X, K, ws, stream);
+            if (rc != GGB_OK) return rc;
+            image = ws;
+        }
+    }
     // half-SM CTAs (two launches resident per SM) whenever the activations leave room for a useful ring
     if (g_force_warps != 16) {
-        const int rc = launch<TYPE, B, T, 8>(W, X, Y, K, N, stream);
+        const int rc = launch<TYPE, B, T, 8>(W, X, Y, K, N, image, stream);
         if (rc != 1 || g_force_warps == 8) return rc;
     }
-    return launch<TYPE, B, T, 16>(W, X, Y, K, N, stream);
+    return launch<TYPE, B, T, 16>(W, X, Y, K, N, image, stream);
 }
 
 template <int TYPE, typename T>
-int dispatch_batch(const void *W, const void *X, void *Y, int64_t B, int64_t K, int64_t N, cudaStream_t stream) {
+int dispatch_batch(const void *W, const void *X, void *Y, int64_t B, int64_t K, int64_t N, void *ws, int64_t ws_bytes, cudaStream_t stream) {
     switch (B) {
-        case 1: return launch_nw<TYPE, 1, T>(W, X, Y, K, N, stream);
-        case 2: return launch_nw<TYPE, 2, T>(W, X, Y, K, N, stream);
-        case 3: return launch_nw<TYPE, 3, T>(W, X, Y, K, N, stream);
-        case 4: return launch_nw<TYPE, 4, T>(W, X, Y, K, N, stream);
+        case 1: return launch_nw<TYPE, 1, T>(W, X, Y, K, N, ws, ws_bytes, stream);
+        case 2: return launch_nw<TYPE, 2, T>(W, X, Y, K, N, ws, ws_bytes, stream);
+        case 3: return launch_nw<TYPE, 3, T>(W, X, Y, K, N, ws, ws_bytes, stream);
+        case 4: return launch_nw<TYPE, 4, T>(W, X, Y, K, N, ws, ws_bytes, stream);
         default: break;
     }
     // IQ4_XS has no tensor-core path behind it and its codebook lookups fill the register file: measured, batches 5-8
     // are faster on the generic kernel (36 vs 43 us at 14336 x 4096, B = 8), so they are not instantiated here
     if constexpr (TYPE != T_IQ4_XS) {
         switch (B) {
-            case 5: return launch_nw<TYPE, 5, T>(W, X, Y, K, N, stream);
-            case 6: return launch_nw<TYPE, 6, T>(W, X, Y, K, N, stream);
-            case 7: return launch_nw<TYPE, 7, T>(W, X, Y, K, N, stream);
-            case 8: return launch_nw<TYPE, 8, T>(W, X, Y, K, N, stream);
+            case 5: return launch_nw<TYPE, 5, T>(W, X, Y, K, N, ws, ws_bytes, stream);
+            case 6: return launch_nw<TYPE, 6, T>(W, X, Y, K, N, ws, ws_bytes, stream);
+            case 7: return launch_nw<TYPE, 7, T>(W, X, Y, K, N, ws, ws_bytes, stream);
+            case 8: return launch_nw<TYPE, 8, T>(W, X, Y, K, N, ws, ws_bytes, stream);
             default: break;
         }
     }
@@ -903,11 +987,12 @@ int dispatch_batch(const void *W, const void *X, void *Y, int64_t B, int64_t K, 
 }
 
 template <int TYPE>
-int dispatch_dtype(const void *W, const void *X, void *Y, int dt, int64_t B, int64_t K, int64_t N, cudaStream_t stream) {
+int dispatch_dtype(const void *W, const void *X, void *Y, int dt, int64_t B, int64_t K, int64_t N, void *ws, int64_t ws_bytes,
+                   cudaStream_t stream) {
     switch (dt) {
-        case GGB_F32:  return dispatch_batch<TYPE, float>(W, X, Y, B, K, N, stream);
-        case GGB_F16:  return dispatch_batch<TYPE, __half>(W, X, Y, B, K, N, stream);
-        case GGB_BF16: return dispatch_batch<TYPE, __nv_bfloat16>(W, X, Y, B, K, N, stream);
+        case GGB_F32:  return dispatch_batch<TYPE, float>(W, X, Y, B, K, N, ws, ws_bytes, stream);
+        case GGB_F16:  return dispatch_batch<TYPE, __half>(W, X, Y, B, K, N, ws, ws_bytes, stream);
+        case GGB_BF16: return dispatch_batch<TYPE, __nv_bfloat16>(W, X, Y, B, K, N, ws, ws_bytes, stream);
         default: return 1;
     }
 }

@@ -154,18 +154,53 @@ class FusedQuantMLP:
     The result equals QuantMLP's bit for bit: rows are independent of how many share a launch, and the SwiGLU is
     computed with torch eager's roundings.  Larger batches / other types fall back to QuantMLP's path."""
 
-    def __init__(self, gate: ColumnParallelQuantLinear, up: ColumnParallelQuantLinear, down: ColumnParallelQuantLinear):
+    def __init__(self, gate: ColumnParallelQuantLinear, up: ColumnParallelQuantLinear, down: ColumnParallelQuantLinear,
+                 W_gu: Optional[torch.Tensor] = None, share_buffers_with: Optional["FusedQuantMLP"] = None):
+        """`W_gu`: the stacked shard [gate.W; up.W] when the caller already holds it (gate.W / up.W are then views of it and
+        nothing is copied).  `share_buffers_with`: another block of the same shapes (the previous layer of a stack) whose
+        two alternating output buffer sets this block uses too -- consecutive blocks alternate between the sets, so a
+        result stays valid until the second-next block runs."""
         if gate.quant_type != up.quant_type or gate.n_total != up.n_total or gate.W.shape[1] != up.W.shape[1]:
             raise ValueError("gate and up must share type and shape")
         self.plain = QuantMLP(gate, up, down)
         self.gate, self.up, self.down = gate, up, down
         self.rank, self.world, self.group = gate.rank, gate.world, gate.group
-        self.W_gu = torch.cat([gate.W, up.W], dim=0).contiguous()        # [2 * I / tp, row_bytes]
+        if W_gu is not None:
+            if W_gu.shape != (2 * gate.n_local, gate.W.shape[1]) or not W_gu.is_contiguous():
+                raise ValueError("W_gu must be the contiguous stack [gate.W; up.W]")
+            self.W_gu = W_gu
+        else:
+            self.W_gu = torch.cat([gate.W, up.W], dim=0).contiguous()    # [2 * I / tp, row_bytes]
         self.inter, self.hidden = gate.n_total, down.n_total
-        self._bufs = {}
-        self._calls = 0
-        self._ws = None
+        if share_buffers_with is not None:
+            o = share_buffers_with
+            if (o.inter, o.hidden, o.world) != (self.inter, self.hidden, self.world):
+                raise ValueError("shared buffers need blocks of the same shape")
+            self._shared = o._shared
+        else:
+            self._shared = {"bufs": {}, "calls": 0, "ws": None}
         self.fused = True
+
+    # the buffer sets, the call counter that alternates them and the workspace live in `_shared` (one per stack of blocks)
+    @property
+    def _bufs(self):
+        return self._shared["bufs"]
+
+    @property
+    def _calls(self):
+        return self._shared["calls"]
+
+    @_calls.setter
+    def _calls(self, v):
+        self._shared["calls"] = v
+
+    @property
+    def _ws(self):
+        return self._shared["ws"]
+
+    @_ws.setter
+    def _ws(self, v):
+        self._shared["ws"] = v
 
     def _buffers(self, dtype, device):
         """per dtype: two (gate|up buffer, down buffer) pairs, each with its peer pointers and barrier handle"""

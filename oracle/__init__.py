@@ -64,6 +64,7 @@ def lib() -> ctypes.CDLL:
         L.orc_mmq_a_operand.argtypes = [vp, ci, i64, vp]
         L.orc_mmvq.argtypes = [vp, ci, vp, i64, i64, i64, vp]
         L.orc_mmq.argtypes = [vp, ci, vp, i64, i64, i64, vp]
+        L.orc_set_num_threads.argtypes = [ci]
         _lib = L
     return _lib
 
@@ -160,6 +161,11 @@ def mmq(w, qtype: int, x: np.ndarray, N: int) -> np.ndarray:
 
 def num_threads() -> int:
     return lib().orc_num_threads()
+
+
+def set_num_threads(n: int) -> int:
+    """OpenMP threads of the multi-threaded oracle entry points (bench legs; torchrun exports OMP_NUM_THREADS=1)."""
+    return lib().orc_set_num_threads(int(n))
 
 
 # ---------------------------------------------------------------- the reference's own CPU op

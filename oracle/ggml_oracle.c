@@ -323,6 +323,17 @@ int orc_num_threads(void) {
 #endif
 }
 
+/* explicit thread count for the bench legs: torchrun exports OMP_NUM_THREADS=1 to its workers */
+int orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
+
 /* ------------------------------------------------------------------ q8_1 activation quantization */
 
 /* One 32-wide group.  amax/sum follow the 5-step xor butterfly of ggml_kernel.cu:34-37:

@@ -38,6 +38,7 @@ int     orc_mmvq(const void *W, int type, const void *q8_1, int64_t B, int64_t K
 int     orc_mmq(const void *W, int type, const void *q8_1_mmq, int64_t M, int64_t K, int64_t N, float *Y);
 
 int     orc_num_threads(void);
+int     orc_set_num_threads(int n);
 
 #ifdef __cplusplus
 }
