@@ -47,6 +47,7 @@ constexpr int A_STAGE_BYTES = BM * 128;
 struct Params {
     const uint8_t *W;
     const uint8_t *Ximg;     // pre-swizzled fp16 B operand image (workspace)
+    const float *row_scale;  // per token: the power of two its image row was divided by (1 for ordinary magnitudes)
     void *Y;
     int64_t N, M, ldy;
     int K;
@@ -156,40 +157,77 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *t
 // exactly the bytes a SWIZZLE_128B TMA load would put in shared memory, so a BN x 64 B tile is ONE
 // contiguous bulk copy.  d8 is rounded to fp16 for the need_sum weight types (it is stored in a half2
 // there, mmq.cu:149-153) and kept in fp32 otherwise.
+// Range: B = fp16(d8 * q8) reaches the token's amax, so a token whose largest activation is outside fp16's comfortable
+// range (the reference keeps int8 quants and fp32 scales: it takes |x| up to ~65504 * 127 and arbitrarily small rows) is
+// stored divided by a power of two 2^e (exact) that brings its amax to [2^8, 2^9); the GEMM's epilogue multiplies the
+// token's outputs by 2^e again (row_scale).  Ordinary rows (2^-8 <= amax <= 2^15) have e = 0 and take no extra work.
 template <typename T, bool D_HALF>
 __global__ void __launch_bounds__(256)
-quantize_b_image_kernel(const T *__restrict__ x, uint8_t *__restrict__ img, int64_t M, int K, int Kp, int Mp, bool vec_ok) {
+quantize_b_image_kernel(const T *__restrict__ x, uint8_t *__restrict__ img, float *__restrict__ row_scale, int64_t M, int K, int Kp,
+                        int Mp, bool vec_ok) {
     ggb_pdl_launch_dependents();        // the GEMM's CTAs may become resident (barriers, TMEM, raw weight tiles) meanwhile
     ggb_pdl_wait();                     // x comes from, and the image may still be read by, the previous kernels
+    __shared__ float s_amax[8];
+    const int64_t row = blockIdx.x;     // one CTA per token
     const int groups_per_row = Kp / 32;
-    const int64_t gid = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 2;
     const int t = threadIdx.x & 3;
-    const int64_t total = M * groups_per_row;
-    const bool live = gid < total;
-    const int64_t row = live ? gid / groups_per_row : 0;
-    const int g = live ? (int)(gid % groups_per_row) : 0;
-    const int k0 = g * 32 + t * 8;
-    float v[8];
-    if (live && k0 + 8 <= K) {
-        load8_f32<T>(x + row * K + k0, vec_ok, v);
-    } else {
+    const T *xr = x + row * K;
+    auto load_group = [&](int g, float (&v)[8]) {
+        const int k0 = g * 32 + t * 8;
+        if (k0 + 8 <= K) {
+            load8_f32<T>(xr + k0, vec_ok, v);
+        } else {
 #pragma unroll
-        for (int i = 0; i < 8; i++) v[i] = (live && k0 + i < K) ? to_f32<T>(x[row * K + k0 + i]) : 0.0f;
-    }
-    const Q8Group r = q8_1_quantize_group<false>(v);
-    if (!live) return;
-    const float d = D_HALF ? __half2float(__float2half_rn(r.d)) : r.d;
-    float y[8];
+            for (int i = 0; i < 8; i++) v[i] = (k0 + i < K) ? to_f32<T>(xr[k0 + i]) : 0.0f;
+        }
+    };
+    // pass 1: the token's amax
+    float amax = 0.0f;
+    for (int g = threadIdx.x >> 2; g < groups_per_row; g += 64) {
+        float v[8];
+        load_group(g, v);
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        y[i] = __fmul_rn(d, (float)(int)(int8_t)(r.q_lo >> (8 * i)));
-        y[i + 4] = __fmul_rn(d, (float)(int)(int8_t)(r.q_hi >> (8 * i)));
+        for (int i = 0; i < 8; i++) amax = fmaxf(amax, fabsf(v[i]));
     }
-    const int ks = k0 >> 6, c = (k0 & 63) >> 3;
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, m));
+    if ((threadIdx.x & 31) == 0) s_amax[threadIdx.x >> 5] = amax;
+    __syncthreads();
+    amax = s_amax[0];
+#pragma unroll
+    for (int w = 1; w < 8; w++) amax = fmaxf(amax, s_amax[w]);
+    int e = 0;
+    if (amax > 32768.0f || (amax < 0.00390625f && amax > 0.0f)) e = ilogbf(amax) - 8;      // NaN / inf rows: e = 0, they propagate
+    if (!(amax <= 3.0e38f)) e = 0;
+    const float inv = ldexpf(1.0f, -e);          // exact: |e| <= 149 + 8
+    if (threadIdx.x == 0) row_scale[row] = ldexpf(1.0f, e);
+    // pass 2 (the row is L1 / L2 resident): q8_1 groups, bit-identical to quantize_mmq_q8_1, folded into fp16
     const int64_t atom = row >> 3;
     const int r8 = (int)(row & 7);
-    uint8_t *dst = img + ((int64_t)ks * (Mp >> 3) + atom) * 1024 + r8 * 128 + ((c ^ r8) << 4);
-    store8(reinterpret_cast<__half *>(dst), y);
+    for (int g0 = 0; g0 < groups_per_row; g0 += 64) {
+        const int g = g0 + (threadIdx.x >> 2);
+        const bool live = g < groups_per_row;
+        float v[8];
+        if (live) {
+            load_group(g, v);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) v[i] = 0.0f;
+        }
+        const Q8Group r = q8_1_quantize_group<false>(v);
+        if (!live) continue;
+        const float d = (D_HALF ? __half2float(__float2half_rn(r.d)) : r.d);
+        float y[8];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            y[i] = __fmul_rn(__fmul_rn(d, (float)(int)(int8_t)(r.q_lo >> (8 * i))), inv);
+            y[i + 4] = __fmul_rn(__fmul_rn(d, (float)(int)(int8_t)(r.q_hi >> (8 * i))), inv);
+        }
+        const int k0 = g * 32 + t * 8;
+        const int ks = k0 >> 6, c = (k0 & 63) >> 3;
+        uint8_t *dst = img + ((int64_t)ks * (Mp >> 3) + atom) * 1024 + r8 * 128 + ((c ^ r8) << 4);
+        store8(reinterpret_cast<__half *>(dst), y);
+    }
 }
 
 // ---------------------------------------------------------------- launch 2: the GEMM
@@ -405,11 +443,25 @@ mmq_kernel(const Params p, const __grid_constant__ CUtensorMap tmapW) {
             T *stage = reinterpret_cast<T *>(smem + p.off_epi);               // [TS tokens][128 weight rows]
             const int et = tid - kFirstEpiWarp * 32;          // 0..127
             const int64_t row0 = (int64_t)rb * BM;
+            // tokens stored divided by a power of two (out-of-range magnitudes, quantize_b_image_kernel): rare, so one vote per tile
+            const int ntok = (int)min((int64_t)NB * BN, p.M - tok0);
+            uint32_t plain = 1u;
+            for (int i = et; i < ntok; i += 128) plain &= (__ldg(p.row_scale + tok0 + i) == 1.0f) ? 1u : 0u;
+            asm volatile("{\n\t.reg .pred pi, po;\n\tsetp.ne.u32 pi, %1, 0;\n\tbar.red.and.pred po, 2, 128, pi;\n\tselp.u32 %0, 1, 0, po;\n\t}"
+                         : "=r"(plain) : "r"(plain) : "memory");
 #pragma unroll 1
             for (int ch = 0; ch < NCH * nb_valid; ch++) {
                 uint32_t v[32];
                 tmem_ld32(taddr + ch * 32, v);        // NB == 2: the second accumulator follows at column ACC_COLS == BN
                 tmem_ld_wait();
+                if (!plain) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const int jt = ch * 32 + j;
+                        const float sc = jt < ntok ? __ldg(p.row_scale + tok0 + jt) : 1.0f;
+                        v[j] = __float_as_uint(__uint_as_float(v[j]) * sc);
+                    }
+                }
                 // The accumulator is weight-row major (one TMEM lane per row): stores straight from it are 64-byte
                 // pieces at a 2 * ldy stride.  Transposed through shared memory, every token row of the tile leaves
                 // as 256 contiguous bytes (fp16) in 16-byte vectors.
@@ -548,11 +600,10 @@ int64_t padded_k(int64_t K) { return (K + RAWK - 1) / RAWK * RAWK; }
 int64_t padded_m(int64_t M) { const int bn = pick_bn(M); return (M + bn - 1) / bn * bn; }
 
 template <typename T>
-int launch_quantize(const void *X, int64_t M, int64_t K, uint8_t *img, bool d_half, cudaStream_t stream) {
+int launch_quantize(const void *X, int64_t M, int64_t K, uint8_t *img, float *row_scale, bool d_half, cudaStream_t stream) {
     const int64_t Kp = padded_k(K), Mp = padded_m(M);
     const bool vec_ok = (reinterpret_cast<uintptr_t>(X) % 16 == 0) && (K % 8 == 0);
-    const int64_t nthreads = M * (Kp / 32) * 4;
-    const int64_t nblk = (nthreads + 255) / 256;
+    const int64_t nblk = M;                       // one CTA per token
     if (nblk > 0x7fffffffLL) {
         ggb_set_error("ggb_mmq: activation matrix too large");
         return GGB_E_SHAPE;
@@ -567,8 +618,8 @@ int launch_quantize(const void *X, int64_t M, int64_t K, uint8_t *img, bool d_ha
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (d_half) GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, quantize_b_image_kernel<T, true>, x, img, M, (int)K, (int)Kp, (int)Mp, vec_ok));
-    else        GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, quantize_b_image_kernel<T, false>, x, img, M, (int)K, (int)Kp, (int)Mp, vec_ok));
+    if (d_half) GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, quantize_b_image_kernel<T, true>, x, img, row_scale, M, (int)K, (int)Kp, (int)Mp, vec_ok));
+    else        GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, quantize_b_image_kernel<T, false>, x, img, row_scale, M, (int)K, (int)Kp, (int)Mp, vec_ok));
     return GGB_OK;
 }
 
@@ -591,7 +642,7 @@ EncodeTiledFn get_encode_fn() {
 // img_plane = token atoms per K-plane of the image (0: this problem's own padded M); tile_limit = cluster-level tiles to
 // run (-1: all)
 template <int TYPE, int BN, int NB, int CL, typename T, bool PAIR = false>
-int launch_gemm(const void *W, const uint8_t *img, void *Y, int64_t M, int64_t K, int64_t N, int64_t ldy, cudaStream_t stream,
+int launch_gemm(const void *W, const uint8_t *img, const float *rscale, void *Y, int64_t M, int64_t K, int64_t N, int64_t ldy, cudaStream_t stream,
                 int img_plane = 0, int tile_limit = -1, bool is_tail = false) {
     constexpr int NSTAGE = PAIR ? 3 : nstage_of(NB);
     constexpr int QK = BlockTraits<TYPE>::QK, BS = BlockTraits<TYPE>::BS;
@@ -600,6 +651,7 @@ int launch_gemm(const void *W, const uint8_t *img, void *Y, int64_t M, int64_t K
     Params p;
     p.W = static_cast<const uint8_t *>(W);
     p.Ximg = img;
+    p.row_scale = rscale;
     p.Y = Y;
     p.N = N;
     p.M = M;
@@ -682,7 +734,8 @@ int launch_gemm(const void *W, const uint8_t *img, void *Y, int64_t M, int64_t K
 
 template <int TYPE, typename T>
 int run_typed(const void *W, const void *X, void *Y, int64_t M, int64_t K, int64_t N, int64_t ldy, uint8_t *img, cudaStream_t stream) {
-    int rc = launch_quantize<T>(X, M, K, img, ggb_mmq_need_sum(TYPE), stream);
+    float *rs = reinterpret_cast<float *>(img + padded_k(K) * padded_m(M) * 2);      // per-token scales follow the image
+    int rc = launch_quantize<T>(X, M, K, img, rs, ggb_mmq_need_sum(TYPE), stream);
     if (rc != GGB_OK) return rc;
     switch (pick_bn(M)) {
         case 256:
@@ -691,7 +744,7 @@ int run_typed(const void *W, const void *X, void *Y, int64_t M, int64_t K, int64
             if (M > 256 && (g_mmq_cfg & 1) == 0 &&
                 ((N + BM - 1) / BM) * ((padded_m(M) / 256 + 1) / 2) >= ggb_device_info().sm_count) {
                 if (g_mmq_cfg & 2) {
-                    rc = launch_gemm<TYPE, 256, 2, 1, T>(W, img, Y, M, K, N, ldy, stream);
+                    rc = launch_gemm<TYPE, 256, 2, 1, T>(W, img, rs, Y, M, K, N, ldy, stream);
                     if (rc != 1) return rc;
                 } else {
                     // Wave quantisation: with 74 clusters, the last round of 128 x 512 tiles is often nearly empty (M = 2048:
@@ -703,25 +756,25 @@ int run_typed(const void *W, const void *X, void *Y, int64_t M, int64_t K, int64
                     const int ntiles = n_rbg * n_tg, rem = ntiles % ncl;
                     const bool tail = (g_mmq_cfg & 4) == 0 && ntiles > ncl && rem > 0 && rem <= n_rbg && rem * 16 <= sms + sms / 4 &&
                                       (K % 256 == 0 || BlockTraits<TYPE>::QK == 32);
-                    rc = (g_mmq_cfg & 8) ? launch_gemm<TYPE, 256, 2, 2, T>(W, img, Y, M, K, N, ldy, stream, 0, tail ? ntiles - rem : -1)
-                                         : launch_gemm<TYPE, 256, 2, 2, T, true>(W, img, Y, M, K, N, ldy, stream, 0, tail ? ntiles - rem : -1);
+                    rc = (g_mmq_cfg & 8) ? launch_gemm<TYPE, 256, 2, 2, T>(W, img, rs, Y, M, K, N, ldy, stream, 0, tail ? ntiles - rem : -1)
+                                         : launch_gemm<TYPE, 256, 2, 2, T, true>(W, img, rs, Y, M, K, N, ldy, stream, 0, tail ? ntiles - rem : -1);
                     if (rc != 1) {
                         if (rc != GGB_OK || !tail) return rc;
                         const int64_t row0 = (int64_t)(n_rbg - rem) * 2 * BM, tok0 = (int64_t)(n_tg - 1) * 512;
                         const int64_t row_bytes = K / BlockTraits<TYPE>::QK * BlockTraits<TYPE>::BS;
-                        return launch_gemm<TYPE, 64, 1, 1, T>(static_cast<const uint8_t *>(W) + row0 * row_bytes, img + (tok0 >> 3) * 1024,
+                        return launch_gemm<TYPE, 64, 1, 1, T>(static_cast<const uint8_t *>(W) + row0 * row_bytes, img + (tok0 >> 3) * 1024, rs + tok0,
                                                               static_cast<T *>(Y) + tok0 * ldy + row0, M - tok0, K, N - row0, ldy, stream,
                                                               (int)(padded_m(M) >> 3), -1, /*is_tail=*/true);
                     }
                 }
             }
             if ((g_mmq_cfg & 2) == 0 && (N + BM - 1) / BM * (padded_m(M) / 256) >= ggb_device_info().sm_count)
-                return launch_gemm<TYPE, 256, 1, 2, T>(W, img, Y, M, K, N, ldy, stream);
-            return launch_gemm<TYPE, 256, 1, 1, T>(W, img, Y, M, K, N, ldy, stream);
-        case 128: return launch_gemm<TYPE, 128, 1, 1, T>(W, img, Y, M, K, N, ldy, stream);
-        case 64:  return launch_gemm<TYPE, 64, 1, 1, T>(W, img, Y, M, K, N, ldy, stream);
-        case 32:  return launch_gemm<TYPE, 32, 1, 1, T>(W, img, Y, M, K, N, ldy, stream);
-        default:  return launch_gemm<TYPE, 16, 1, 1, T>(W, img, Y, M, K, N, ldy, stream);
+                return launch_gemm<TYPE, 256, 1, 2, T>(W, img, rs, Y, M, K, N, ldy, stream);
+            return launch_gemm<TYPE, 256, 1, 1, T>(W, img, rs, Y, M, K, N, ldy, stream);
+        case 128: return launch_gemm<TYPE, 128, 1, 1, T>(W, img, rs, Y, M, K, N, ldy, stream);
+        case 64:  return launch_gemm<TYPE, 64, 1, 1, T>(W, img, rs, Y, M, K, N, ldy, stream);
+        case 32:  return launch_gemm<TYPE, 32, 1, 1, T>(W, img, rs, Y, M, K, N, ldy, stream);
+        default:  return launch_gemm<TYPE, 16, 1, 1, T>(W, img, rs, Y, M, K, N, ldy, stream);
     }
 }
 
@@ -742,7 +795,7 @@ int run_dtype(const void *W, const void *X, void *Y, int dt, int64_t M, int64_t 
 void ggb_mmq_tune(int cfg) { g_mmq_cfg = cfg; }
 
 int64_t ggb_mmq_workspace_bytes_impl(int, int64_t M, int64_t K, int64_t) {
-    return padded_k(K) * padded_m(M) * 2;       // the fp16 B-operand image
+    return padded_k(K) * padded_m(M) * 2 + padded_m(M) * 4;       // the fp16 B-operand image + one fp32 scale per token
 }
 
 int ggb_mmq_impl(const void *W, const void *X, void *Y, int type, int xy_dtype, int64_t M, int64_t K, int64_t N,

@@ -142,6 +142,12 @@ int         ggb_mmvq_fused(const void *W, const void *X, const void *X2, int64_t
  * Replaces ggml_mul_mat_a8 (ggml/mmq.cu:180-255): quantize_mmq_q8_1_cuda + mul_mat_q
  * (ggml/mmq.cuh:1917-2031).  `ws` must hold ggb_mmq_workspace_bytes(...) bytes (the quantized
  * activations; the reference allocates them with torch::empty on every call, ggml/mmq.cu:207-208).
+ * Numerics: the tensor cores multiply fp16 operands, A = fp16(dequantize(W)), B = fp16(d8 * q8) with the q8_1
+ * quantization of the reference, fp32 accumulation (one extra 2^-11 relative rounding per operand).
+ * Range: activations of ANY fp32 / bf16 magnitude -- a token whose largest |x| is outside [2^-8, 2^15] is stored
+ * divided by a power of two and its outputs are multiplied back (exact); weights must dequantize to |w| <= 65504
+ * (fp16), which every real GGUF tensor does by orders of magnitude.  Launches: the activation image kernel, the GEMM,
+ * and for some (M, N) a second GEMM launch over the last partial round of tiles -- all programmatic dependent launches.
  */
 int64_t     ggb_mmq_workspace_bytes(int type, int64_t M, int64_t K, int64_t N);
 int         ggb_mmq(const void *W, const void *X, void *Y, int type, int xy_dtype,

@@ -137,6 +137,67 @@ def test_config4_full_shape_properties(ops, t):
         assert np.abs(got - want).max() <= 2.0 ** -9 * scale + 2.0 ** -10 * np.abs(want).max()
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16], ids=["f16", "bf16"])
+@pytest.mark.parametrize("shape", [(14336, 4096), (4096, 14336), (4096, 4096)], ids=["14336x4096", "4096x14336", "4096x4096"])
+@pytest.mark.parametrize("M", [512, 1024, 4096, 8192])
+@pytest.mark.parametrize("t", [oracle.Q4_K, oracle.Q6_K], ids=["Q4_K", "Q6_K"])
+def test_config4_every_benchmarked_shape(ops, t, M, shape, dtype):
+    """Every (type, M, shape, dtype) bench_extras times (BASELINE config 4): sampled 64 x 64 blocks against the oracle --
+    first / middle / last row blocks x first / last token tiles, which covers every tile-picker branch (one or two
+    256-token tiles per weight stage, clusters, CTA pairs) and the rectangle a tail launch covers."""
+    N, K = shape
+    w_np = oracle.random_weights(t, N, K, seed=M + N)
+    w = torch.from_numpy(w_np).cuda()
+    x = (torch.randn(M, K, generator=torch.Generator().manual_seed(M)) * 0.5).to(dtype).cuda()
+    y = ops.ggml_mul_mat_a8(w, x, t, N)
+    assert y.shape == (M, N) and bool(torch.isfinite(y).all())
+    ulp = OUT_REL[dtype]
+    for r0 in (0, (N // 2 // 64) * 64 + 64, N - 64, N - 320):
+        for t0 in (0, M - 64, M // 2):
+            rows, toks = slice(r0, r0 + 64), slice(t0, t0 + 64)
+            want = oracle.mmq(w_np[rows], t, x[toks].float().cpu().numpy(), 64)
+            got = y[toks, rows].float().cpu().numpy()
+            scale = np.abs(want).max()
+            err = np.abs(got - want)
+            assert (err <= 2.0 ** -9 * scale + 1.01 * ulp * np.abs(want)).all(), \
+                f"{oracle.TYPE_NAMES[t]} M={M} {N}x{K} {dtype} rows {r0} tokens {t0}: max err {err.max():.3e} scale {scale:.3e}"
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("t", [oracle.Q4_K, oracle.Q6_K, oracle.Q8_0, oracle.Q5_0, oracle.Q2_K], ids=["Q4_K", "Q6_K", "Q8_0", "Q5_0", "Q2_K"])
+def test_activation_magnitude_range(ops, t, dtype):
+    """The reference keeps int8 quants and fp32 scales, so it takes activations far outside fp16's range; the kernel's B
+    operand is fp16(d8 * q8), stored per token divided by a power of two when the token's amax is outside [2^-8, 2^15] and
+    multiplied back in the epilogue (exact).  Token rows of wildly different magnitudes in ONE call: every row within the
+    usual tolerance of ITS OWN scale, nothing non-finite.  (Round-1 advisor finding: 1e5 used to give inf / NaN rows.)
+    Q4_1 / Q5_1 are left out: the reference multiplies (d, m) by (d8, s8) in half precision (mmq.cuh:528), which is only
+    good to ~0.5 % as soon as d * d8 is an fp16 subnormal -- there is no accurate reference value to compare with."""
+    N, K = 384, 2048
+    mags = [1e5, 3.0e38 ** 0.5, 1.0, 1e-6, 1e-12, 7e4, 2.0 ** -9, 0.0, 6.0e4, 1e-30]
+    if oracle.mmq_need_sum(t):
+        # these types carry half2(d8, sum x) in the reference's q8_1_mmq blocks (mmq.cu:149-153): its own range ends where
+        # the fp16 sum of 32 inputs overflows (|x| ~ 3e3) and where d8 = amax / 127 becomes an fp16 subnormal (|x| ~ 1e-2),
+        # so the comparison stays inside (the kernel rounds d8 to fp16 like the reference, its minima use d8 * sum(q8))
+        mags = [3e3, 1.0, 0.05, 2.0 ** -4, 0.0, 1e3, 30.0, 0.5]
+    M = 83
+    w_np = oracle.random_weights(t, N, K, seed=5)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(M, K, generator=g)
+    for i in range(M):
+        x[i] *= mags[i % len(mags)]
+    x = x.to(dtype)
+    x32 = x.float().numpy()
+    got = ops.ggml_mul_mat_a8(torch.from_numpy(w_np).cuda(), x.cuda(), t, N).float().cpu().numpy()
+    want = oracle.mmq(w_np, t, x32, N)
+    assert np.isfinite(want).all()
+    assert np.isfinite(got).all(), f"non-finite outputs in token rows {sorted(set(np.argwhere(~np.isfinite(got))[:, 0].tolist()))}"
+    for i in range(M):
+        scale = np.abs(want[i]).max()
+        err = np.abs(got[i] - want[i])
+        tol = 2.0 ** -9 * scale + 1.01 * OUT_REL[dtype] * np.abs(want[i]) + 1e-44
+        assert (err <= tol).all(), f"{oracle.TYPE_NAMES[t]} {dtype} token {i} (x ~ {mags[i % len(mags)]:.1e}): err {err.max():.3e} scale {scale:.3e}"
+
+
 def test_errors(ops):
     w = torch.zeros(144 * 4, dtype=torch.uint8, device="cuda")
     with pytest.raises(ValueError):
