@@ -280,6 +280,16 @@ int ggb_mmvq_gather(const void *W, const void *X, int type, int xy_dtype, int64_
                           stream);
 }
 
+int ggb_mmvq_fused_supported(int type, int64_t B, int64_t K) {
+    if (B < 1 || B > 8 || K <= 0 || K % 256 != 0) return 0;
+    switch (type) {
+        case T_Q4_K: case T_Q5_K: return 1;
+        case T_IQ4_XS: return (K % 512 == 0 && B <= 4) ? 1 : 0; // 136-byte super-blocks; batches 5-8 run on the generic kernel
+        case T_Q6_K: return K % 2048 == 0 ? 1 : 0;          // 210-byte super-blocks: rows are 16-byte aligned every 8 of them
+        default: return 0;
+    }
+}
+
 int64_t ggb_mmvq_workspace_bytes(int type, int64_t B, int64_t K, int64_t N) {
     if (block_elems(type) == 0 || B <= 0 || K <= 0 || N <= 0) return 0;
     return ggb_mmvq_workspace_bytes_impl(type, B, K, N);

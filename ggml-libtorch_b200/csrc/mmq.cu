@@ -12,15 +12,19 @@
 //     A[i,k] = fp16( dequantize(W)[i,k] )        -- bit-identical to ggml_dequantize(..., fp16)
 //     B[j,k] = fp16( d8[j,k/32] * q8[j,k] )      -- the q8_1 quantization of X (bit-identical d8/q8)
 //     Y[j,i] = sum_k A[i,k] * B[j,k]             -- tcgen05.mma.kind::f16, fp32 accumulate in TMEM
-// Two launches: (1) quantize X to q8_1 and write the fp16 B operand as a pre-swizzled tile image into the
-// workspace; (2) the persistent warp-specialised GEMM:
-//     warp 0      producer: cp.async.bulk of raw GGUF row segments (128 rows x 256 columns per raw stage)
-//                 and of B tiles (one contiguous, pre-swizzled BN x 64 image per stage), mbarrier tx-count
-//     warps 6-13  unpack: raw bytes -> fp16 A tile in the 128-byte-swizzle K-major layout UMMA reads
-//     warp 1      one elected thread issues tcgen05.mma (M=128 weight rows, N=BN tokens, K=16) x4 per
-//                 stage and tcgen05.commit's the stage / the accumulator
-//     warps 2-5   epilogue: tcgen05.ld the fp32 accumulator (double-buffered in the 512 TMEM columns, so
-//                 it overlaps the next tile's MMAs), convert, store Y
+// Launches: (1) quantize X to q8_1 and write the fp16 B operand as a pre-swizzled tile image into the workspace (one CTA
+// per token; a token of out-of-range magnitude is stored divided by a power of two, undone in the epilogue); (2) the
+// persistent warp-specialised GEMM; (3) for some (M, N) the last partial round of tiles as a second GEMM launch of
+// 128 x 64 tiles.  The GEMM for M > 256 runs as CTA PAIRS (cluster of 2): the two CTAs own two adjacent 128-row blocks and
+// the leader issues ONE tcgen05.mma.cta_group::2 (M = 256 weight rows, N = 256 tokens, K = 16) per step for both; each
+// CTA supplies its own unpacked A tile and half of the B tile.  Per CTA (14 warps):
+//     warp 0      producer: 2-D TMA of raw GGUF row segments (128 rows x 256 columns per raw stage) and bulk copies of
+//                 this CTA's part of each pre-swizzled B tile, mbarrier tx-count
+//     warps 6-13  unpack: raw bytes -> fp16 A tile in the 128-byte-swizzle K-major layout UMMA reads (half2 arithmetic)
+//     warp 1      one elected thread issues the MMAs and tcgen05.commit's the stage / the accumulator (pair: the peer's
+//                 MMA warp relays "my A and my half of B are in place" with a remote mbarrier arrive)
+//     warps 2-5   epilogue: tcgen05.ld the fp32 accumulator, convert, transpose through an 8 KB staging buffer, store
+//                 256-byte token rows of Y in 16-byte vectors
 // Roofline: tensor pipe (dense fp16 -> fp32 accumulate); ops = 2*M*N*K.
 #include <cuda.h>          // CUtensorMap (types only: the encode entry point is fetched at run time)
 

@@ -29,7 +29,7 @@ void ggb_mmvq_sb_set_static_weights(int on) { g_pdl_prefetch = on ? 1 : 0; }
 int ggb_mmvq_static_weights() { return g_pdl_prefetch; }
 int ggb_static_weights() { return g_pdl_prefetch; }
 int ggb_mmvq_l2_prefetch_mb() { return g_l2_prefetch_mb; }
-extern "C" void ggb_debug_mmvq_trace(void *device_buffer) {      // debug only: 8 * 256 u64 per launch
+extern "C" void ggb_debug_mmvq_trace(void *device_buffer) {      // debug only (declared in ggml_b200.h): 8 * 256 u64 per launch
     g_trace = static_cast<unsigned long long *>(device_buffer);
     g_trace_launch = 0;
 }

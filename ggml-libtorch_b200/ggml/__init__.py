@@ -6,8 +6,9 @@ Same three public functions, same positional signatures:
     ggml_mul_mat_vec_a8(W, X, quant_type, row)      -> Tensor [B, row]   (MMVQ, 1 <= B <= 8)
     ggml_mul_mat_a8(W, X, quant_type, row)          -> Tensor [..., row] (MMQ, X 2-D or 3-D)
 
-The ops are registered with torch.library (namespace `ggml_b200`, CUDA only, with fake kernels so
-meta tracing works) and call hand-written sm_100a CUDA through the C ABI of libggml_b200.so
+The ops are registered with torch.library (namespace `ggml_b200`, the reference's schemas, CUDA only, with
+fake kernels so meta tracing works; `register_reference_namespace()` also defines them as `torch.ops._ggml.*`)
+and call hand-written sm_100a CUDA through the C ABI of libggml_b200.so
 (include/ggml_b200.h).  PyTorch supplies device memory and streams only.  There is no CPU path:
 non-CUDA tensors raise.
 """
@@ -23,7 +24,8 @@ __all__ = [
     "ggml_dequantize", "ggml_mul_mat_vec_a8", "ggml_mul_mat_a8", "ggml_quantize_q8_1",
     "dequantize_out", "mul_mat_vec_a8_out", "mul_mat_a8_out", "mmq_workspace_bytes", "mmvq_workspace_bytes",
     "set_option", "GGB_OPT_STATIC_WEIGHTS", "mul_mat_vec_a8_gather", "mul_mat_vec_a8_fused",
-    "block_elems", "block_bytes", "SUPPORTED_TYPES", "MMQ_TYPES", "MMVQ_MAX_BATCH",
+    "block_elems", "block_bytes", "SUPPORTED_TYPES", "MMQ_TYPES", "MMVQ_MAX_BATCH", "mmvq_fused_supported",
+    "register_reference_namespace",
 ]
 
 _lib = _capi.lib
@@ -221,29 +223,31 @@ def mul_mat_a8_out(W: torch.Tensor, X2d: torch.Tensor, quant_type: int, row: int
 # torch.library registration (schemas follow torch-ext/torch_binding.cpp:6-21)
 # ------------------------------------------------------------------------------------------------
 
-@torch.library.custom_op("ggml_b200::ggml_dequantize", mutates_args=(), device_types="cuda")
-def _op_dequantize(W: torch.Tensor, type: int, m: int, n: int, out_dtype: int) -> torch.Tensor:
+# Explicit schema strings (torch.library.custom_op would infer `SymInt type` from the Python annotation; the reference
+# declares `int type`): identical to torch-ext/torch_binding.cpp:8-19.
+_LIB = torch.library.Library("ggml_b200", "DEF")
+_LIB.define("ggml_dequantize(Tensor W, int type, SymInt m, SymInt n) -> Tensor")
+_LIB.define("ggml_mul_mat_vec_a8(Tensor W, Tensor X, int type, SymInt row) -> Tensor")
+_LIB.define("ggml_mul_mat_a8(Tensor W, Tensor X, int type, SymInt row) -> Tensor")
+# extension (no reference counterpart): the cast the reference's callers do afterwards, fused; out_dtype = GGB_F32/F16/BF16
+_LIB.define("ggml_dequantize_dtype(Tensor W, int type, SymInt m, SymInt n, int out_dtype) -> Tensor")
+
+
+def _op_dequantize(W: torch.Tensor, type: int, m: int, n: int) -> torch.Tensor:
+    out = torch.empty((m, n), dtype=torch.float16, device=W.device)      # fp16 like the reference CUDA op
+    return dequantize_out(W, type, m, n, out)
+
+
+def _op_dequantize_dtype(W: torch.Tensor, type: int, m: int, n: int, out_dtype: int) -> torch.Tensor:
     out = torch.empty((m, n), dtype=_DT_INV[out_dtype], device=W.device)
     return dequantize_out(W, type, m, n, out)
 
 
-@_op_dequantize.register_fake
-def _(W, type, m, n, out_dtype):
-    return torch.empty((m, n), dtype=_DT_INV[out_dtype], device=W.device)
-
-
-@torch.library.custom_op("ggml_b200::ggml_mul_mat_vec_a8", mutates_args=(), device_types="cuda")
 def _op_mmvq(W: torch.Tensor, X: torch.Tensor, type: int, row: int) -> torch.Tensor:
     out = torch.empty((X.shape[0], row), dtype=X.dtype, device=W.device)
     return mul_mat_vec_a8_out(W, X, type, row, out)
 
 
-@_op_mmvq.register_fake
-def _(W, X, type, row):
-    return torch.empty((X.shape[0], row), dtype=X.dtype, device=W.device)
-
-
-@torch.library.custom_op("ggml_b200::ggml_mul_mat_a8", mutates_args=(), device_types="cuda")
 def _op_mmq(W: torch.Tensor, X: torch.Tensor, type: int, row: int) -> torch.Tensor:
     # X 2-D [M, K] or 3-D [B, T, K] flattened to B*T rows, as ggml/mmq.cu:183-204
     if X.dim() not in (2, 3):
@@ -255,7 +259,29 @@ def _op_mmq(W: torch.Tensor, X: torch.Tensor, type: int, row: int) -> torch.Tens
     return out.view(*lead, row)
 
 
-@_op_mmq.register_fake
+# CUDA dispatch key only, like the reference (torch_binding.cpp:10,15,20); fake kernels so meta tracing / torch.compile see shapes
+_LIB.impl("ggml_dequantize", _op_dequantize, "CUDA")
+_LIB.impl("ggml_dequantize_dtype", _op_dequantize_dtype, "CUDA")
+_LIB.impl("ggml_mul_mat_vec_a8", _op_mmvq, "CUDA")
+_LIB.impl("ggml_mul_mat_a8", _op_mmq, "CUDA")
+
+
+@torch.library.register_fake("ggml_b200::ggml_dequantize")
+def _(W, type, m, n):
+    return torch.empty((m, n), dtype=torch.float16, device=W.device)
+
+
+@torch.library.register_fake("ggml_b200::ggml_dequantize_dtype")
+def _(W, type, m, n, out_dtype):
+    return torch.empty((m, n), dtype=_DT_INV[out_dtype], device=W.device)
+
+
+@torch.library.register_fake("ggml_b200::ggml_mul_mat_vec_a8")
+def _(W, X, type, row):
+    return torch.empty((X.shape[0], row), dtype=X.dtype, device=W.device)
+
+
+@torch.library.register_fake("ggml_b200::ggml_mul_mat_a8")
 def _(W, X, type, row):
     return torch.empty((*X.shape[:-1], row), dtype=X.dtype, device=W.device)
 
@@ -271,7 +297,9 @@ def ggml_dequantize(W: torch.Tensor, quant_type: int, m: int, n: int, dtype: tor
     if dtype not in _DT:
         raise ValueError(f"ggml_dequantize: unsupported output dtype {dtype}")
     _check_w(W, quant_type, int(m), int(n), "ggml_dequantize")
-    return torch.ops.ggml_b200.ggml_dequantize(W, int(quant_type), int(m), int(n), _DT[dtype])
+    if dtype == torch.float16:
+        return torch.ops.ggml_b200.ggml_dequantize(W, int(quant_type), int(m), int(n))
+    return torch.ops.ggml_b200.ggml_dequantize_dtype(W, int(quant_type), int(m), int(n), _DT[dtype])
 
 
 def ggml_mul_mat_vec_a8(W: torch.Tensor, X: torch.Tensor, quant_type: int, row: int) -> torch.Tensor:
@@ -285,3 +313,26 @@ def ggml_mul_mat_vec_a8(W: torch.Tensor, X: torch.Tensor, quant_type: int, row: 
 def ggml_mul_mat_a8(W: torch.Tensor, X: torch.Tensor, quant_type: int, row: int) -> torch.Tensor:
     """Mulmat through the MMQ kernel for arbitrary batch size."""
     return torch.ops.ggml_b200.ggml_mul_mat_a8(W, X, int(quant_type), int(row))
+
+
+def mmvq_fused_supported(quant_type: int, B: int, K: int) -> bool:
+    """Pure query: is (type, batch, K) on the fused-epilogue path of mul_mat_vec_a8_gather / _fused?"""
+    return bool(_lib.ggb_mmvq_fused_supported(int(quant_type), int(B), int(K)))
+
+
+def register_reference_namespace(namespace: str = "_ggml") -> None:
+    """Also expose the three ops as torch.ops.<namespace>.* with the reference's exact schemas
+    (torch-ext/torch_binding.cpp:6-21; its TORCH_EXTENSION_NAME is `_ggml` in development builds), so that callers which
+    go through torch.ops instead of the Python functions are drop-in too.  Opt-in: defining the namespace while the
+    reference's own extension is loaded would be a duplicate registration."""
+    lib = torch.library.Library(namespace, "FRAGMENT")
+    lib.define("ggml_dequantize(Tensor W, int type, SymInt m, SymInt n) -> Tensor")
+    lib.define("ggml_mul_mat_vec_a8(Tensor W, Tensor X, int type, SymInt row) -> Tensor")
+    lib.define("ggml_mul_mat_a8(Tensor W, Tensor X, int type, SymInt row) -> Tensor")
+    lib.impl("ggml_dequantize", lambda W, type, m, n: torch.ops.ggml_b200.ggml_dequantize(W, type, m, n), "CUDA")
+    lib.impl("ggml_mul_mat_vec_a8", lambda W, X, type, row: torch.ops.ggml_b200.ggml_mul_mat_vec_a8(W, X, type, row), "CUDA")
+    lib.impl("ggml_mul_mat_a8", lambda W, X, type, row: torch.ops.ggml_b200.ggml_mul_mat_a8(W, X, type, row), "CUDA")
+    _REF_NS_LIBS.append(lib)            # keep the registration alive
+
+
+_REF_NS_LIBS: list = []

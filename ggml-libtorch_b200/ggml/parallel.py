@@ -91,12 +91,9 @@ class ColumnParallelQuantLinear:
         need = mmvq_workspace_bytes(self.quant_type, M, K, self.n_local)
         if need and (self._ws is None or self._ws.numel() < need):
             self._ws = torch.empty(need, dtype=torch.uint8, device=X.device)
-        try:
-            mul_mat_vec_a8_gather(self.W, X, self.quant_type, self.n_local, ptrs, self.n_total, self.rank * self.n_local,
-                                  self._ws)
-        except ValueError:
-            self.fused_gather = False        # this type / shape is not on the fused path (same verdict on every rank)
-            return None
+        # (eligibility was decided from (type, batch, K) alone in forward(): the same verdict on every rank.  Any error here
+        # is a real one -- misaligned pointer, workspace -- and must surface instead of silently changing the exchange.)
+        mul_mat_vec_a8_gather(self.W, X, self.quant_type, self.n_local, ptrs, self.n_total, self.rank * self.n_local, self._ws)
         self._calls += 1
         hdl.barrier(channel=0)               # every rank's slice has landed in this rank's copy
         return buf[:M]
@@ -107,9 +104,9 @@ class ColumnParallelQuantLinear:
 
     def forward(self, X: torch.Tensor) -> torch.Tensor:
         if self.fused_gather and X.dim() == 2 and X.shape[0] <= 8:
-            y = self._forward_fused(X)
-            if y is not None:
-                return y
+            from . import mmvq_fused_supported
+            if mmvq_fused_supported(self.quant_type, X.shape[0], X.shape[1]):
+                return self._forward_fused(X)
         y_local = self.local(X)
         if self.world == 1:
             return y_local
@@ -225,19 +222,18 @@ class FusedQuantMLP:
     def forward(self, X: torch.Tensor) -> torch.Tensor:
         if not (self.fused and X.dim() == 2 and X.shape[0] <= 8):
             return self.plain(X)
-        from . import mmvq_workspace_bytes, mul_mat_vec_a8_fused
+        from . import mmvq_fused_supported, mmvq_workspace_bytes, mul_mat_vec_a8_fused
         M, K = X.shape
+        # eligibility from (type, batch, K) alone: the same verdict on every rank, decided before anything is launched
+        if not (mmvq_fused_supported(self.gate.quant_type, M, K) and mmvq_fused_supported(self.down.quant_type, M, self.inter)):
+            return self.plain(X)
         (gu, gu_h, gu_p), (dn, dn_h, dn_p) = self._buffers(X.dtype, X.device)[self._calls & 1]
         n_gu, n_dn, I = self.gate.n_local, self.down.n_local, self.inter
         need = max(mmvq_workspace_bytes(self.gate.quant_type, M, K, 2 * n_gu), mmvq_workspace_bytes(self.down.quant_type, M, I, n_dn))
         if need and (self._ws is None or self._ws.numel() < need):
             self._ws = torch.empty(need, dtype=torch.uint8, device=X.device)
-        try:
-            mul_mat_vec_a8_fused(self.W_gu, X, None, self.gate.quant_type, 2 * n_gu, gu_p, 2 * I, self.rank * n_gu,
-                                 n_gu, I + self.rank * n_gu, self._ws)
-        except ValueError:
-            self.fused = False                   # not on the fused path (same verdict on every rank, nothing launched)
-            return self.plain(X)
+        mul_mat_vec_a8_fused(self.W_gu, X, None, self.gate.quant_type, 2 * n_gu, gu_p, 2 * I, self.rank * n_gu,
+                             n_gu, I + self.rank * n_gu, self._ws)
         if gu_h is not None:
             gu_h.barrier(channel=0)
         mul_mat_vec_a8_fused(self.down.W, gu[:M, :I], gu[:M, I:], self.down.quant_type, n_dn, dn_p, self.hidden,

@@ -61,7 +61,7 @@ const char *ggb_last_error(void);
  * Default 0: everything waits for the previous kernel.
  */
 enum ggb_option {
-    GGB_OPT_STATIC_WEIGHTS = 1,
+    GGB_OPT_STATIC_WEIGHTS = 1,   /* see above; honoured by every kernel that streams weights: dequantize, all MMVQ kernels, MMQ */
     GGB_OPT_MMVQ_WARPS = 2,    /* tuning/debug: value = warps (0 auto, 8, 16) | shared-memory cap in KB << 8 */
     GGB_OPT_MMQ_TILES = 3,     /* tuning/debug bits: 1 = one 256-token tile per weight stage, 2 = no clusters, 4 = no tail launch, 8 = no CTA-pair MMA (0 = automatic) */
     GGB_OPT_MMVQ_MMA = 5,      /* tuning/debug: super-blocks per chunk | (log2 K-split + 1) << 8 | minimum batch << 16 (0 fields = automatic) */
@@ -71,6 +71,16 @@ enum ggb_option {
     GGB_OPT_MMVQ_L2_PREFETCH = 4 /* MB of weights per MMVQ launch pulled into L2 while the previous kernel drains (default 0 = off) */
 };
 int         ggb_set_option(int option, int value);
+/* Options and tuning knobs are process-wide plain integers shared by all devices and threads: set them once, before
+ * any concurrent use of the library (the matmul / dequantize entry points themselves are re-entrant and stateless). */
+
+/* Debug only: per-CTA timestamps of the following MMVQ launches are written to `device_buffer` (8 * 256 uint64 per
+ * launch, scripts/mmvq_trace.py); NULL switches it off.  Not part of the drop-in surface. */
+void        ggb_debug_mmvq_trace(void *device_buffer);
+
+/* 1 when (type, B, K) is on the fused-epilogue path of ggb_mmvq_gather / ggb_mmvq_fused, else 0: a pure query, the
+ * same on every rank, so a tensor-parallel caller decides ONCE whether to use the fused exchange. */
+int         ggb_mmvq_fused_supported(int type, int64_t B, int64_t K);
 
 /* Block geometry of a ggml_type (0 if unsupported).  ggml/ggml-common.h:1163-1240 (qk) / :17-108. */
 int         ggb_block_elems(int type);
@@ -101,8 +111,12 @@ int         ggb_quantize_q8_1(const void *X, int x_dtype, int64_t rows, int64_t 
 /*
  * MMVQ: Y[B, N] = q8_1(X[B, K]) . W[N, K]^T, 1 <= B <= 8 (the reference allows B == 1 only).
  * Replaces ggml_mul_mat_vec_a8 (ggml/ggml_kernel.cu:80-193): quantize_row_q8_1_cuda + mul_mat_vec_q
- * (ggml/mmvq.cuh:2-38) in ONE launch -- activations are quantized to q8_1 inside the kernel.
- * X and Y share `xy_dtype`.  No workspace is needed (ws may be NULL); the query returns 0.
+ * (ggml/mmvq.cuh:2-38).  X and Y share `xy_dtype`.
+ * Launches: batches 1-2 (and every batch of the types without a tensor-core path) are ONE launch -- the activations are
+ * quantized to q8_1 inside the GEMV kernel; batches 3-8 of Q4_K / Q5_K / Q6_K / IQ4_NL / IQ4_XS (2-8 for K > 8192) are TWO
+ * programmatic-dependent launches: the q8_1 activation image is written once into `ws`, then the tensor-core GEMV reads
+ * it (in-kernel it was repeated by all 148 CTAs).  `ws` must hold ggb_mmvq_workspace_bytes(type, B, K, N) bytes (0 for
+ * the one-launch cases with K < 4096; a few KB otherwise); it is scratch: nothing survives the call.
  */
 int64_t     ggb_mmvq_workspace_bytes(int type, int64_t B, int64_t K, int64_t N);
 int         ggb_mmvq(const void *W, const void *X, void *Y, int type, int xy_dtype,

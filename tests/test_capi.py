@@ -94,10 +94,36 @@ def test_fake_tensor_shapes():
         X = torch.empty(3, 5, 256, dtype=torch.bfloat16, device="cuda")
         y = torch.ops.ggml_b200.ggml_mul_mat_a8(W, X, 12, 8)
         assert y.shape == (3, 5, 8) and y.dtype == torch.bfloat16
-        d = torch.ops.ggml_b200.ggml_dequantize(W, 12, 8, 256, 1)
+        d = torch.ops.ggml_b200.ggml_dequantize(W, 12, 8, 256)           # the reference's 4-argument schema, fp16 out
         assert d.shape == (8, 256) and d.dtype == torch.float16
+        d = torch.ops.ggml_b200.ggml_dequantize_dtype(W, 12, 8, 256, 2)  # extension: fused cast (GGB_BF16)
+        assert d.shape == (8, 256) and d.dtype == torch.bfloat16
         v = torch.ops.ggml_b200.ggml_mul_mat_vec_a8(W, X[0, :2], 12, 8)
         assert v.shape == (2, 8)
+
+
+def test_reference_schemas_and_namespace():
+    """The three ops carry the reference's schemas (torch-ext/torch_binding.cpp:6-21) and can be exposed under its
+    development namespace `_ggml` as well."""
+    import torch
+    import ggml
+    want = {"ggml_dequantize": "(Tensor W, int type, SymInt m, SymInt n) -> Tensor",
+            "ggml_mul_mat_vec_a8": "(Tensor W, Tensor X, int type, SymInt row) -> Tensor",
+            "ggml_mul_mat_a8": "(Tensor W, Tensor X, int type, SymInt row) -> Tensor"}
+    if not hasattr(torch.ops._ggml, "ggml_dequantize"):
+        ggml.register_reference_namespace("_ggml")
+    for name, sig in want.items():
+        ours = str(getattr(torch.ops.ggml_b200, name).default._schema)
+        assert ours == f"ggml_b200::{name}{sig}", ours
+        ref = str(getattr(torch.ops._ggml, name).default._schema)
+        assert ref.split("::")[1] == f"{name}{sig}", ref
+
+
+def test_fused_supported_query(capi):
+    L = capi.lib
+    assert L.ggb_mmvq_fused_supported(12, 1, 8192) == 1 and L.ggb_mmvq_fused_supported(14, 8, 28672) == 1
+    assert L.ggb_mmvq_fused_supported(14, 1, 4352) == 0          # Q6_K rows not 16-byte aligned
+    assert L.ggb_mmvq_fused_supported(2, 1, 4096) == 0 and L.ggb_mmvq_fused_supported(12, 9, 4096) == 0
 
 
 def test_iq4_types_and_options_without_gpu(capi):

@@ -81,13 +81,46 @@ def test_reference_style_mmvq(ops, t, dtype, hidden_size):
         torch.testing.assert_close(output, ref_output, atol=MMVQ_ATOL, rtol=MMVQ_RTOL)
 
 
+def _check_sampled(ops, t, N, K, B, dtype, seed=0, nsample=192):
+    """Full-size GEMV on the GPU, oracle on a sample of rows (rows are independent: a row's value does not depend on
+    which rows share the launch -- test_linearity_property): first / last rows of the matrix and rows around every
+    boundary a CTA's row range can have, plus random ones."""
+    w = oracle.random_weights(t, N, K, seed=seed + t)
+    x = torch.randn(B, K, generator=torch.Generator().manual_seed(seed)).to(dtype)
+    got = ops.ggml_mul_mat_vec_a8(torch.from_numpy(w).cuda(), x.cuda(), t, N)
+    assert got.shape == (B, N) and got.dtype == dtype and bool(torch.isfinite(got).all())
+    rng = np.random.default_rng(seed)
+    rows = np.unique(np.concatenate([np.arange(min(16, N)), np.arange(max(0, N - 16), N),
+                                     (np.arange(1, 148)[:, None] * N // 148 + np.arange(-1, 1)[None, :]).ravel() % N,
+                                     rng.integers(0, N, size=nsample)]))
+    want = oracle.mmvq(w[rows], t, x.float().numpy(), len(rows))
+    g = got.float().cpu().numpy()[:, rows]
+    scale = float(np.abs(want).max()) + 1e-30
+    tol = 2e-5 * scale + OUT_REL[dtype] * np.abs(want) * 1.01
+    bad = np.abs(g - want) > tol
+    assert not bad.any(), (f"{oracle.TYPE_NAMES[t]} N={N} K={K} B={B} {dtype}: {bad.sum()} of {bad.size} sampled values off; "
+                           f"max err {np.abs(g - want).max():.3e} scale {scale:.3e}")
+
+
+@pytest.mark.parametrize("B", [1, 2, 3, 4, 5, 6, 7, 8])
 @pytest.mark.parametrize("t", [oracle.Q4_K, oracle.Q6_K], ids=["Q4_K", "Q6_K"])
-@pytest.mark.parametrize("shape", [(14336, 4096), (4096, 14336)])
-def test_config3_llama8b_shapes(ops, t, shape):
-    """BASELINE config 3: Llama-3-8B Q4_K_M decode GEMV shapes, batch 1 and 8, fp16."""
+@pytest.mark.parametrize("shape", [(14336, 4096), (4096, 14336)], ids=["14336x4096", "4096x14336"])
+def test_config3_llama8b_shapes(ops, t, shape, B):
+    """BASELINE config 3: Llama-3-8B Q4_K_M decode GEMV shapes at full size, EVERY batch 1..8 (each batch can take a
+    different kernel: register-resident batch 1, dp4a ring batch 2, tensor-core batches 3-8 / 2-8 for K > 8192), fp16."""
     N, K = shape
-    for B in (1, 8):
-        _check(ops, t, N, K, B, torch.float16, seed=B)
+    _check_sampled(ops, t, N, K, B, torch.float16, seed=B)
+
+
+@pytest.mark.parametrize("B", [1, 8])
+@pytest.mark.parametrize("tp", [1, 2, 4, 8])
+@pytest.mark.parametrize("proj", ["gate_up_Q4_K", "down_Q4_K", "down_Q6_K"])
+def test_config5_llama70b_shard_shapes(ops, proj, tp, B):
+    """BASELINE config 5: the per-rank shard shapes of the Llama-3-70B MLP for tp = 1, 2, 4, 8 (gate/up [28672/tp, 8192],
+    down [8192/tp, 28672]; the stacked gate|up shard of the fused block has 2 * 28672/tp rows), batch 1 and 8."""
+    t, N, K = {"gate_up_Q4_K": (oracle.Q4_K, 2 * 28672 // tp, 8192), "down_Q4_K": (oracle.Q4_K, 8192 // tp, 28672),
+               "down_Q6_K": (oracle.Q6_K, 8192 // tp, 28672)}[proj]
+    _check_sampled(ops, t, N, K, B, torch.float16, seed=tp + B)
 
 
 @pytest.mark.parametrize("case", [(oracle.Q4_K, 130, 28672, 8), (oracle.Q6_K, 70, 14336, 8), (oracle.Q6_K, 40, 28672, 6),

@@ -1,7 +1,7 @@
-"""GPU parity of the column-parallel layers: world_size 2 over NCCL, the product's CUDA
+"""GPU parity of the column-parallel layers: world_size 2, 4 and 8 over NCCL, the product's CUDA
 kernels on every rank.  The sharded MLP output must equal the single-GPU output bit for bit for decode
 (M = 1, 8: MMVQ) and prefill (M = 160: MMQ), because every output element is produced by exactly one rank
-with the same K order as on one GPU.  Skipped on boxes with fewer than two GPUs."""
+with the same K order as on one GPU.  Each world size is skipped on boxes with fewer GPUs."""
 import os
 import socket
 
@@ -78,11 +78,11 @@ def _worker(rank, world, port, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.timeout(600)
-def test_column_parallel_world2_nccl(tmp_path):
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs")
-    world = 2
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_column_parallel_nccl(tmp_path, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     mp.start_processes(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True, start_method="spawn")
     # single-GPU result of the same layer stack
     import ggml
@@ -91,12 +91,13 @@ def test_column_parallel_world2_nccl(tmp_path):
     wg, wu, wd = _weights(HIDDEN, INTER)
     mk = lambda w, tt, n: ColumnParallelQuantLinear(w.to(dev), tt, n, 0, 1)
     mlp = QuantMLP(mk(wg, oracle.Q4_K, INTER), mk(wu, oracle.Q4_K, INTER), mk(wd, oracle.Q6_K, HIDDEN))
-    r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
+    ranks = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
+    r0 = ranks[0]
     for M in BATCHES:
         x = _inputs(M).to(dev)
         want_gate = mlp.gate(x).float().cpu().numpy()
         want_mlp = mlp(x).float().cpu().numpy()
-        for r in (r0, r1):
+        for r in ranks:
             assert np.array_equal(r[f"gate{M}"], want_gate), f"gate M={M}: sharded != single-GPU"
             assert np.array_equal(r[f"mlp{M}"], want_mlp), f"mlp M={M}: sharded != single-GPU"
             assert np.array_equal(r[f"fused{M}"], want_mlp), f"mlp M={M}: fused gather != single-GPU"

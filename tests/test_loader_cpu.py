@@ -51,3 +51,36 @@ def test_load_whole_and_sharded(tmp_path):
                 assert np.array_equal(p[name].data.numpy(), w)
     with pytest.raises(ValueError):
         load_gguf(path, device="cpu", rank=0, world=3)
+
+
+def test_unsupported_quant_types_are_not_dropped_silently(tmp_path):
+    """Advisor finding (round 1): a model with IQ2 / IQ3 tensors used to load with layers missing and no error."""
+    pytest.importorskip("torch")
+    pytest.importorskip("ggml", reason="the package needs libggml_b200.so")
+    from ggml.loader import UnsupportedQuantTypes, load_gguf
+    path = str(tmp_path / "mixed.gguf")
+    wr = gguf.GGUFWriter(path, "llama")
+    wr.add_tensor("blk.0.ffn_gate_64x256", oracle.random_weights(oracle.Q4_K, 64, 256, seed=1), raw_dtype=gguf.GGMLQuantizationType(12))
+    iq2 = np.zeros((4, 256 // 256 * 66), dtype=np.uint8)                 # IQ2_XXS: 66 bytes per 256 values
+    wr.add_tensor("blk.0.ffn_up_4x256", iq2, raw_dtype=gguf.GGMLQuantizationType.IQ2_XXS)
+    wr.add_tensor("norm.weight", np.ones(256, dtype=np.float32))
+    wr.write_header_to_file(); wr.write_kv_data_to_file(); wr.write_tensors_to_file(); wr.close()
+    with pytest.raises(UnsupportedQuantTypes, match="ffn_up"):
+        load_gguf(path, device="cpu")
+    skipped = []
+    got = load_gguf(path, device="cpu", strict=False, skipped=skipped)
+    assert set(got) == {"blk.0.ffn_gate_64x256"} and [n for n, _ in skipped] == ["blk.0.ffn_up_4x256"]
+
+
+def test_expert_stack_is_flattened(tmp_path):
+    """A 3-D tensor (MoE expert stack) loads as experts * rows independent weight rows instead of aborting the file."""
+    pytest.importorskip("torch")
+    pytest.importorskip("ggml", reason="the package needs libggml_b200.so")
+    from ggml.loader import load_gguf
+    path = str(tmp_path / "moe.gguf")
+    w = oracle.random_weights(oracle.Q4_K, 4 * 32, 256, seed=3)           # 4 experts x 32 rows x 256 columns
+    wr = gguf.GGUFWriter(path, "llama")
+    wr.add_tensor("blk.0.ffn_gate_exps", w.reshape(4, 32, -1), raw_dtype=gguf.GGMLQuantizationType(12))
+    wr.write_header_to_file(); wr.write_kv_data_to_file(); wr.write_tensors_to_file(); wr.close()
+    q = load_gguf(path, device="cpu")["blk.0.ffn_gate_exps"]
+    assert (q.rows, q.cols) == (128, 256) and np.array_equal(q.data.numpy(), w)
