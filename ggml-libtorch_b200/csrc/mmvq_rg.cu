@@ -33,6 +33,7 @@ unsigned long long *ggb_mmvq_trace_slot();
 namespace {
 
 constexpr int kNW = 12;                  // warps per CTA
+constexpr int kDefaultCluster = 2;       // CTAs sharing one activation quantization (measured)
 constexpr int kChunkItems = 32;          // items (128 values) per row chunk = one per lane
 
 struct RgParams {
@@ -44,7 +45,7 @@ struct RgParams {
     int K, nsb, ipr, row_bytes;
     int C;               // chunks per row
     int RW;              // row lanes per CTA = kNW / C
-    int off_scales, off_part, off_slots;
+    int off_scales, off_part, off_bar, off_slots;
     int spc;             // super-blocks per chunk
     int early;           // rows per warp requested before the dependency wait (static weights), 1..kStages
     long long wstep;     // bytes between two consecutive rows of a warp = RW * row_bytes
@@ -79,6 +80,28 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
     return v;
+}
+
+// ---- thread-block cluster helpers: the CTAs of a cluster share the activation quantization through distributed shared memory
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t mapa(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+// asynchronous remote stores that count their bytes on an mbarrier of the DESTINATION CTA: the reader waits on its own
+// barrier for the image's byte count.  (A barrier.cluster with release semantics instead also waits for the stores of the
+// ~100 KB of cp.async weight requests in flight: measured 2400-3900 cycles per launch.)
+__device__ __forceinline__ void st_async_v2(uint32_t addr, uint32_t x, uint32_t y, uint32_t mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];"
+                 ::"r"(addr), "r"(x), "r"(y), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void st_async_f32(uint32_t addr, float x, uint32_t mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+                 ::"r"(addr), "r"(__float_as_uint(x)), "r"(mbar) : "memory");
 }
 
 template <int TYPE> struct RgOps;
@@ -177,6 +200,20 @@ mmvq_rg_kernel(const RgParams p) {
     unsigned long long *tr = p.trace ? p.trace + blockIdx.x * 8 : nullptr;
     if (tr && tid == 0) { tr[7] = gtime(); tr[0] = clk64(); }
     ggb_pdl_launch_dependents();
+    // Cluster of CL CTAs (launch attribute; CL = 1: none): each CTA quantizes 1 / CL of the activation row and writes its part
+    // into every CTA's shared memory (DSMEM), so the row is read from L2 and quantized CL times less often per SM.  The
+    // arrive here / wait before the first remote store proves that every CTA of the cluster has started.
+    const uint32_t CL = p.image == nullptr ? cluster_nctarank() : 1u, crank = CL > 1 ? cluster_ctarank() : 0u;
+    uint64_t *act_bar = reinterpret_cast<uint64_t *>(smem + p.off_bar);        // counts the bytes of the image as they land (CL > 1)
+    if (CL > 1) {
+        if (tid == 0) {
+            mbar_init(act_bar, 1);
+            fence_mbar_init();
+            mbar_expect_tx(act_bar, (uint32_t)(p.K + p.K / 4));                // quants + (d8, d8 * sum q8) per 32-value group
+        }
+        __syncthreads();
+        cluster_arrive();          // (before any weight request is in flight: nothing for the release to wait for)
+    }
 
     // warp -> (chunk c, row lane rl): rows rl, rl + RW, ... of this CTA's range, chunk c of each
     const int c = warp % C, rl = warp / C;
@@ -236,7 +273,11 @@ mmvq_rg_kernel(const RgParams p) {
     // 4 lanes per 32-value group, U groups per thread and pass (U = 4 on long rows: the pass is a latency chain of loads,
     // shuffles and a division, and every CTA repeats the whole row)
     const T *X = static_cast<const T *>(p.X);
-    const int ngroups_row = p.K >> 5;
+    const int ngroups_all = p.K >> 5;
+    // this CTA's share of the groups: [g_first, ngroups_row)
+    const int g_share = (ngroups_all + (int)CL - 1) / (int)CL;
+    const int g_first = (int)crank * g_share, ngroups_row = min(ngroups_all, g_first + g_share);
+    const uint32_t act_q_s = smem_u32(act_q), act_s_s = smem_u32(act_s);
     constexpr int GPI = (kNW * 32) / 4;
     auto quantize_pass = [&](auto u_tag, int base, bool first) {
         constexpr int U = decltype(u_tag)::value;
@@ -258,6 +299,7 @@ mmvq_rg_kernel(const RgParams p) {
             for (int s = 0; s < S; s++)
                 if (s >= early) issue_row(my_ring_s + s * stage_bytes);
             if (tr && tid == 0) tr[2] = clk64() + (long long)(v[0][0] == 123.456f);      // after the first X loads have landed
+            if (CL > 1) cluster_wait();                           // every CTA of the cluster runs: its shared memory may be written
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
@@ -270,12 +312,26 @@ mmvq_rg_kernel(const RgParams p) {
             if (g < ngroups_row) {
                 const int it = g >> 2, j = g & 3;
                 const int i = 2 * j + (t4 >> 1);
-                uint8_t *dst = reinterpret_cast<uint8_t *>(act_q + i * ipr + it) + 8 * (t4 & 1);
-                *reinterpret_cast<uint2 *>(dst) = make_uint2(q.q_lo, q.q_hi);
-                if (t4 == 0) {
-                    const float d8 = __half2float(__float2half_rn(q.d));
-                    reinterpret_cast<float *>(act_s + it)[j] = d8;
-                    reinterpret_cast<float *>(act_s + ipr + it)[j] = d8 * (float)(mine + other);
+                const float d8 = __half2float(__float2half_rn(q.d));
+                if (CL == 1) {
+                    uint8_t *dst = reinterpret_cast<uint8_t *>(act_q + i * ipr + it) + 8 * (t4 & 1);
+                    *reinterpret_cast<uint2 *>(dst) = make_uint2(q.q_lo, q.q_hi);
+                    if (t4 == 0) {
+                        reinterpret_cast<float *>(act_s + it)[j] = d8;
+                        reinterpret_cast<float *>(act_s + ipr + it)[j] = d8 * (float)(mine + other);
+                    }
+                } else {
+                    const uint32_t qa = act_q_s + (uint32_t)(i * ipr + it) * 16u + 8u * (t4 & 1);
+                    const uint32_t sa = act_s_s + (uint32_t)it * 16u + 4u * j;
+                    const uint32_t bar_s = smem_u32(act_bar);
+                    for (uint32_t r = 0; r < CL; r++) {           // the same bytes into every CTA of the cluster (its own included)
+                        const uint32_t mb = mapa(bar_s, r);
+                        st_async_v2(mapa(qa, r), q.q_lo, q.q_hi, mb);
+                        if (t4 == 0) {
+                            st_async_f32(mapa(sa, r), d8, mb);
+                            st_async_f32(mapa(sa + (uint32_t)ipr * 16u, r), d8 * (float)(mine + other), mb);
+                        }
+                    }
                 }
             }
         }
@@ -303,13 +359,17 @@ mmvq_rg_kernel(const RgParams p) {
         }
         if (tr && tid == 0) { tr[2] = clk64(); tr[3] = tr[2]; }
     } else {
-    if (ngroups_row > 2 * GPI) {
-        for (int base = 0; base < ngroups_row; base += 4 * GPI) quantize_pass(std::integral_constant<int, 4>{}, base, base == 0);
+    if (ngroups_row - g_first > 2 * GPI) {
+        for (int base = g_first; base < ngroups_row || base == g_first; base += 4 * GPI) quantize_pass(std::integral_constant<int, 4>{}, base, base == g_first);
     } else {
-        for (int base = 0; base < ngroups_row; base += 2 * GPI) quantize_pass(std::integral_constant<int, 2>{}, base, base == 0);
+        for (int base = g_first; base < ngroups_row || base == g_first; base += 2 * GPI) quantize_pass(std::integral_constant<int, 2>{}, base, base == g_first);
     }
     if (tr && tid == 0) tr[3] = clk64();
-    __syncthreads();
+    if (CL > 1) {
+        mbar_wait(act_bar, 0);     // every CTA's part has landed in this CTA's shared memory
+    } else {
+        __syncthreads();
+    }
 
     // this lane's item of every row chunk it will see: activations -> registers
     if (live) {
@@ -391,7 +451,7 @@ mmvq_rg_kernel(const RgParams p) {
 }
 
 template <int TYPE, typename T, int S, bool FULL>
-int launch_cfg(RgParams &p, int grid, int smem, cudaStream_t stream) {
+int launch_cfg(RgParams &p, int grid, int smem, int cluster, cudaStream_t stream) {
     const DeviceInfo &di = ggb_device_info();
     static bool attr_set[64] = {};               // per instantiation and device; idempotent, so a race is harmless
     if (!attr_set[di.dev]) {
@@ -403,11 +463,15 @@ int launch_cfg(RgParams &p, int grid, int smem, cudaStream_t stream) {
     cfg.blockDim = dim3(kNW * 32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = (unsigned)cluster;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = cluster > 1 ? 2 : 1;
     GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmvq_rg_kernel<TYPE, T, S, FULL>, p));
     return GGB_OK;
 }
@@ -438,12 +502,19 @@ int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, const vo
     p.dbg = (ggb_sb::g_rg_mode >> 8) & 0xff;
     p.early = (ggb_sb::g_rg_mode >> 16) & 0xf;
     const int64_t max_ctas = (N + p.RW - 1) / p.RW;
-    const int grid = (int)(max_ctas < di.sm_count ? max_ctas : di.sm_count);
+    int grid = (int)(max_ctas < di.sm_count ? max_ctas : di.sm_count);
+    // CTAs per cluster sharing the activation quantization (debug bits 20..23 of the mode: 1, 2 or 4; default below)
+    int cluster = (ggb_sb::g_rg_mode >> 20) & 0xf;
+    if (cluster != 1 && cluster != 2 && cluster != 4) cluster = K >= 8192 ? kDefaultCluster : 1;   // short rows: the pass is a latency chain, splitting it gains nothing
+    if (image != nullptr || grid < 2 * cluster) cluster = 1;
+    grid = (grid + cluster - 1) / cluster * cluster;       // (CTAs past the last row quantize their share and exit)
+    if (grid > di.sm_count) grid -= cluster;
     p.part_rows = p.C > 1 ? (int)((N + grid - 1) / grid + 1) : 0;
     if ((int64_t)p.part_rows * p.C * 4 > 16384) return 1;
     p.off_scales = ((int)K + 15) & ~15;
     p.off_part = p.off_scales + 2 * p.ipr * 16;
-    p.off_slots = (p.off_part + p.part_rows * p.C * 4 + 127) & ~127;
+    p.off_bar = (p.off_part + p.part_rows * p.C * 4 + 7) & ~7;                // (only a cluster launch uses it)
+    p.off_slots = (p.off_bar + (cluster > 1 ? 8 : 0) + 127) & ~127;
     const int half_sm = (di.max_smem_optin + 1024) / 2 - 1024;               // two CTAs per SM
     const bool full = p.nsb % 16 == 0;
     const int force_s = (ggb_sb::g_rg_mode >> 12) & 0xf;                     // debug: 3 or 4 stages
@@ -455,8 +526,8 @@ int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, const vo
     if (probe_only) return 2;
     if (p.early == 0 || p.early > S) p.early = 1;
     p.trace = ggb_mmvq_trace_slot();
-    if (S == 4) return full ? launch_cfg<TYPE, T, 4, true>(p, grid, smem, stream) : launch_cfg<TYPE, T, 4, false>(p, grid, smem, stream);
-    return full ? launch_cfg<TYPE, T, 3, true>(p, grid, smem, stream) : launch_cfg<TYPE, T, 3, false>(p, grid, smem, stream);
+    if (S == 4) return full ? launch_cfg<TYPE, T, 4, true>(p, grid, smem, cluster, stream) : launch_cfg<TYPE, T, 4, false>(p, grid, smem, cluster, stream);
+    return full ? launch_cfg<TYPE, T, 3, true>(p, grid, smem, cluster, stream) : launch_cfg<TYPE, T, 3, false>(p, grid, smem, cluster, stream);
 }
 
 template <int TYPE>

@@ -107,7 +107,10 @@ class ColumnParallelQuantLinear:
             from . import mmvq_fused_supported
             if mmvq_fused_supported(self.quant_type, X.shape[0], X.shape[1]):
                 return self._forward_fused(X)
-        y_local = self.local(X)
+        return self.gather(self.local(X))
+
+    def gather(self, y_local: torch.Tensor) -> torch.Tensor:
+        """All-gather of the ranks' column slices [M, N/tp] into the full [M, N] (NCCL over NVLink)."""
         if self.world == 1:
             return y_local
         M = y_local.shape[0]
@@ -132,6 +135,12 @@ class QuantMLP:
         self.gate, self.up, self.down = gate, up, down
 
     def forward(self, X: torch.Tensor) -> torch.Tensor:
+        if self.gate.world > 1 and not (self.gate.fused_gather and X.dim() == 2 and X.shape[0] <= 8):
+            # SwiGLU is elementwise: each rank applies it to ITS column slices of g and u, and only h is exchanged --
+            # one all-gather of [M, I] instead of two, and 1/tp of the elementwise work (bit-identical: the same ops
+            # on the same values, whichever rank holds them)
+            h_local = torch.nn.functional.silu(self.gate.local(X)) * self.up.local(X)
+            return self.down(self.gate.gather(h_local))
         g = self.gate(X)
         u = self.up(X)
         h = torch.nn.functional.silu(g) * u
