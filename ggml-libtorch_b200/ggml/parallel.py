@@ -47,6 +47,38 @@ def _default_matmul(W: torch.Tensor, X: torch.Tensor, quant_type: int, rows: int
     return ggml_mul_mat_a8(W, X, quant_type, rows)
 
 
+class TpBarrier:
+    """The barrier of the fused exchange as ONE programmatic-dependent launch of the library (ggb_tp_barrier) instead of
+    a separate barrier kernel of the framework: a symmetric block of 16 uint32 per rank (slot r = the last epoch rank r
+    reached, word 8 = this rank's epoch counter on the device, so CUDA-graph replays need nothing from the host).
+    Collective construction (every rank of `group`)."""
+
+    def __init__(self, rank: int, world: int, group, device: torch.device):
+        import ctypes
+
+        import torch.distributed._symmetric_memory as symm_mem
+        self.rank, self.world = rank, world
+        self.flags = symm_mem.empty(16, dtype=torch.int32, device=device)
+        self.flags.zero_()
+        self.hdl = symm_mem.rendezvous(self.flags, group if group is not None else dist.group.WORLD)
+        torch.cuda.current_stream(device).synchronize()
+        self.hdl.barrier(channel=0)                     # every rank's block is zero before anybody signals
+        torch.cuda.current_stream(device).synchronize()
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self._arr = (ctypes.c_void_p * world)(*ptrs)
+        self.device = device
+
+    def __call__(self) -> None:
+        from . import _capi, _stream
+        with torch.cuda.device(self.device):
+            rc = _capi.lib.ggb_tp_barrier(self._arr, self.world, self.rank, _stream(self.flags))
+        _capi.check(rc, "ggb_tp_barrier")
+
+    def lost_peer(self) -> int:
+        """0, or 1 + the rank that never arrived at some barrier (checked by tests; reading it synchronises)."""
+        return int(self.flags[9].item())
+
+
 class ColumnParallelQuantLinear:
     """y = x @ dequant(W).T with W [N, K] row-sharded over the ranks of `group`.
 
@@ -69,6 +101,7 @@ class ColumnParallelQuantLinear:
         self._symm = {}          # dtype -> [(buffer, handle, peer pointers)] x 2
         self._calls = 0
         self._ws = None
+        self._barrier = None
 
     def _symm_buffers(self, dtype: torch.dtype, device: torch.device):
         """Two symmetric [MMVQ_MAX_BATCH, N] buffers per dtype (collective on first use: every rank calls it)."""
@@ -95,7 +128,11 @@ class ColumnParallelQuantLinear:
         # is a real one -- misaligned pointer, workspace -- and must surface instead of silently changing the exchange.)
         mul_mat_vec_a8_gather(self.W, X, self.quant_type, self.n_local, ptrs, self.n_total, self.rank * self.n_local, self._ws)
         self._calls += 1
-        hdl.barrier(channel=0)               # every rank's slice has landed in this rank's copy
+        if self._barrier is None:
+            import os
+            self._barrier = (lambda: hdl.barrier(channel=0)) if os.environ.get("GGML_B200_TP_BARRIER", "") == "torch" else \
+                TpBarrier(self.rank, self.world, self.group, X.device)
+        self._barrier()                      # every rank's slice has landed in this rank's copy
         return buf[:M]
 
     def local(self, X: torch.Tensor) -> torch.Tensor:
@@ -184,7 +221,7 @@ class FusedQuantMLP:
                 raise ValueError("shared buffers need blocks of the same shape")
             self._shared = o._shared
         else:
-            self._shared = {"bufs": {}, "calls": 0, "ws": None}
+            self._shared = {"bufs": {}, "calls": 0, "ws": None, "barrier": None}
         self.fused = True
 
     # the buffer sets, the call counter that alternates them and the workspace live in `_shared` (one per stack of blocks)
@@ -207,6 +244,19 @@ class FusedQuantMLP:
     @_ws.setter
     def _ws(self, v):
         self._shared["ws"] = v
+
+    def _barrier(self, device):
+        """the stack's barrier: ggb_tp_barrier (one PDL launch) unless GGML_B200_TP_BARRIER=torch asks for the framework's"""
+        b = self._shared["barrier"]
+        if b is None:
+            import os
+            if os.environ.get("GGML_B200_TP_BARRIER", "") == "torch":
+                hdl = self._buffers(torch.float16, device)[0][0][1]
+                b = lambda: hdl.barrier(channel=0)
+            else:
+                b = TpBarrier(self.rank, self.world, self.group, device)
+            self._shared["barrier"] = b
+        return b
 
     def _buffers(self, dtype, device):
         """per dtype: two (gate|up buffer, down buffer) pairs, each with its peer pointers and barrier handle"""
@@ -243,12 +293,13 @@ class FusedQuantMLP:
             self._ws = torch.empty(need, dtype=torch.uint8, device=X.device)
         mul_mat_vec_a8_fused(self.W_gu, X, None, self.gate.quant_type, 2 * n_gu, gu_p, 2 * I, self.rank * n_gu,
                              n_gu, I + self.rank * n_gu, self._ws)
-        if gu_h is not None:
-            gu_h.barrier(channel=0)
+        barrier = self._barrier(X.device) if gu_h is not None else None
+        if barrier is not None:
+            barrier()                            # every rank's gate | up slices have landed in this rank's copy
         mul_mat_vec_a8_fused(self.down.W, gu[:M, :I], gu[:M, I:], self.down.quant_type, n_dn, dn_p, self.hidden,
                              self.rank * n_dn, 0, 0, self._ws)
-        if dn_h is not None:
-            dn_h.barrier(channel=0)
+        if barrier is not None:
+            barrier()
         self._calls += 1
         return dn[:M]
 

@@ -152,6 +152,14 @@ int         ggb_mmvq_fused(const void *W, const void *X, const void *X2, int64_t
                            void *ws, int64_t ws_bytes, void *stream);
 
 /*
+ * Cross-rank barrier of a tensor-parallel group on the stream, as one programmatic-dependent launch (the barrier the fused
+ * exchange above needs before the gathered buffer is read; no reference counterpart).  flag_peers[i] = rank i's copy of a
+ * symmetric block of 16 uint32, zero-initialised once, as mapped on this rank; every rank calls it the same number of
+ * times.  Word 9 of the rank's own block is set when a peer never arrived (the wait is bounded).  Graph-capturable.
+ */
+int         ggb_tp_barrier(void *const *flag_peers, int n_peers, int rank, void *stream);
+
+/*
  * MMQ: Y[M, N] (row stride ldy elements) = q8_1_mmq(X[M, K]) . W[N, K]^T.
  * Replaces ggml_mul_mat_a8 (ggml/mmq.cu:180-255): quantize_mmq_q8_1_cuda + mul_mat_q
  * (ggml/mmq.cuh:1917-2031).  `ws` must hold ggb_mmq_workspace_bytes(...) bytes (the quantized
