@@ -65,6 +65,7 @@ static int block_elems(int type) {
         case T_Q2_K: case T_Q3_K: case T_Q4_K: case T_Q5_K: case T_Q6_K: return 256;
         case T_IQ4_NL: return 32;
         case T_IQ4_XS: return 256;
+        case T_IQ2_XXS: case T_IQ2_XS: case T_IQ2_S: case T_IQ3_XXS: case T_IQ3_S: case T_IQ1_S: case T_IQ1_M: return 256;
         default: return 0;
     }
 }
@@ -75,7 +76,17 @@ static int block_bytes(int type) {
         case T_Q2_K: return 84;  case T_Q3_K: return 110; case T_Q4_K: return 144;
         case T_Q5_K: return 176; case T_Q6_K: return 210;
         case T_IQ4_NL: return 18; case T_IQ4_XS: return 136;
+        case T_IQ2_XXS: return 66; case T_IQ2_XS: return 74; case T_IQ2_S: return 82;
+        case T_IQ3_XXS: return 98; case T_IQ3_S: return 110; case T_IQ1_S: return 50; case T_IQ1_M: return 56;
         default: return 0;
+    }
+}
+
+static bool mmq_has_no_case(int type) {      // the IQ formats: dequantize + MMVQ only (the reference's mmq.cu:222-252 has no case either)
+    switch (type) {
+        case T_IQ4_NL: case T_IQ4_XS: case T_IQ2_XXS: case T_IQ2_XS: case T_IQ2_S: case T_IQ3_XXS: case T_IQ3_S: case T_IQ1_S:
+        case T_IQ1_M: return true;
+        default: return false;
     }
 }
 
@@ -314,14 +325,14 @@ int ggb_mmvq(const void *W, const void *X, void *Y, int type, int xy_dtype, int6
 }
 
 int64_t ggb_mmq_workspace_bytes(int type, int64_t M, int64_t K, int64_t N) {
-    if (block_elems(type) == 0 || type == T_IQ4_NL || type == T_IQ4_XS || M <= 0 || K <= 0 || N <= 0) return 0;
+    if (block_elems(type) == 0 || mmq_has_no_case(type) || M <= 0 || K <= 0 || N <= 0) return 0;
     return ggb_mmq_workspace_bytes_impl(type, M, K, N);
 }
 
 int ggb_mmq(const void *W, const void *X, void *Y, int type, int xy_dtype, int64_t M, int64_t K, int64_t N,
             int64_t ldy, void *ws, int64_t ws_bytes, void *stream) {
     g_err[0] = 0;
-    if (type == T_IQ4_NL || type == T_IQ4_XS) {
+    if (mmq_has_no_case(type)) {
         // the reference's ggml_mul_mat_a8 has no case for the IQ types (mmq.cu:222-252 leaves Y uninitialised)
         ggb_set_error("ggb_mmq: ggml type %d has dequantize and MMVQ only (no MMQ in the reference either)", type);
         return GGB_E_TYPE;

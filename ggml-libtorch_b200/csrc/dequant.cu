@@ -19,6 +19,7 @@
 //      64-byte segments.
 // Algorithmic bytes per value: block_bytes/QK read + sizeof(out) written.
 #include "unpack_col.cuh"
+#include "unpack_iq.cuh"
 
 namespace {
 
@@ -68,7 +69,7 @@ dequant_tile_kernel(const uint8_t *__restrict__ W, OutT *__restrict__ out, int64
     }
 
     OutT *dst = out + b0 * QK;
-    if constexpr (QK == 256 && TYPE != T_IQ4_XS) {
+    if constexpr (QK == 256 && TYPE != T_IQ4_XS && !kIsIqGrid<TYPE>) {
         // K-quants: decode every (d*sc, dmin*m) pair of the tile ONCE into a table, then one "column unit" = 8
         // consecutive bytes of a block and all the 16 / 32 values packed in them (unpack_col.cuh).
         using CU = ColUnpack<TYPE>;
@@ -93,7 +94,7 @@ dequant_tile_kernel(const uint8_t *__restrict__ W, OutT *__restrict__ out, int64
             store8(dst + ((int64_t)blk * ITEMS_PER_BLOCK + p) * 8, y);
         }
     } else {
-        // legacy types, IQ4_NL and IQ4_XS (a warp per super-block).  item = 8 consecutive values.  Thread t always handles octet p = t % ITEMS_PER_BLOCK of blocks
+        // legacy types, IQ4_NL, IQ4_XS and the codebook IQ formats (a warp per super-block).  item = 8 consecutive values.  Thread t always handles octet p = t % ITEMS_PER_BLOCK of blocks
         // t / ITEMS_PER_BLOCK + k * BLK_STEP, so everything derived from p (shifts, byte offsets) is loop-invariant;
         // consecutive threads write consecutive 16-byte chunks (a warp store covers 512 contiguous bytes).
         constexpr int BLK_STEP = kThreads / ITEMS_PER_BLOCK;
@@ -164,6 +165,13 @@ int ggb_dequantize_impl(const void *W, int type, int64_t nelem, void *out, int o
         case T_Q6_K: return dispatch_dtype<T_Q6_K>(W, out, nelem, out_dtype, stream);
         case T_IQ4_NL: return dispatch_dtype<T_IQ4_NL>(W, out, nelem, out_dtype, stream);
         case T_IQ4_XS: return dispatch_dtype<T_IQ4_XS>(W, out, nelem, out_dtype, stream);
+        case T_IQ2_XXS: return dispatch_dtype<T_IQ2_XXS>(W, out, nelem, out_dtype, stream);
+        case T_IQ2_XS: return dispatch_dtype<T_IQ2_XS>(W, out, nelem, out_dtype, stream);
+        case T_IQ2_S: return dispatch_dtype<T_IQ2_S>(W, out, nelem, out_dtype, stream);
+        case T_IQ3_XXS: return dispatch_dtype<T_IQ3_XXS>(W, out, nelem, out_dtype, stream);
+        case T_IQ3_S: return dispatch_dtype<T_IQ3_S>(W, out, nelem, out_dtype, stream);
+        case T_IQ1_S: return dispatch_dtype<T_IQ1_S>(W, out, nelem, out_dtype, stream);
+        case T_IQ1_M: return dispatch_dtype<T_IQ1_M>(W, out, nelem, out_dtype, stream);
         default:
             ggb_set_error("ggb_dequantize: unsupported ggml type %d", type);
             return GGB_E_TYPE;

@@ -12,7 +12,9 @@
 enum : int {
     T_Q4_0 = 2, T_Q4_1 = 3, T_Q5_0 = 6, T_Q5_1 = 7, T_Q8_0 = 8,
     T_Q2_K = 10, T_Q3_K = 11, T_Q4_K = 12, T_Q5_K = 13, T_Q6_K = 14,
-    T_IQ4_NL = 20, T_IQ4_XS = 23          // dequantize + MMVQ only, like the reference (no MMQ case: mmq.cu:222-252)
+    T_IQ4_NL = 20, T_IQ4_XS = 23,         // dequantize + MMVQ only, like the reference (no MMQ case: mmq.cu:222-252)
+    // the codebook formats (iq_grid.cuh): dequantize + MMVQ only as well
+    T_IQ2_XXS = 16, T_IQ2_XS = 17, T_IQ3_XXS = 18, T_IQ1_S = 19, T_IQ3_S = 21, T_IQ2_S = 22, T_IQ1_M = 29
 };
 
 template <int TYPE> struct BlockTraits;
@@ -28,6 +30,15 @@ template <> struct BlockTraits<T_Q5_K> { static constexpr int QK = 256, BS = 176
 template <> struct BlockTraits<T_Q6_K> { static constexpr int QK = 256, BS = 210; };
 template <> struct BlockTraits<T_IQ4_NL> { static constexpr int QK = 32,  BS = 18;  };
 template <> struct BlockTraits<T_IQ4_XS> { static constexpr int QK = 256, BS = 136; };
+template <> struct BlockTraits<T_IQ2_XXS> { static constexpr int QK = 256, BS = 66;  };
+template <> struct BlockTraits<T_IQ2_XS>  { static constexpr int QK = 256, BS = 74;  };
+template <> struct BlockTraits<T_IQ2_S>   { static constexpr int QK = 256, BS = 82;  };
+template <> struct BlockTraits<T_IQ3_XXS> { static constexpr int QK = 256, BS = 98;  };
+template <> struct BlockTraits<T_IQ3_S>   { static constexpr int QK = 256, BS = 110; };
+template <> struct BlockTraits<T_IQ1_S>   { static constexpr int QK = 256, BS = 50;  };
+template <> struct BlockTraits<T_IQ1_M>   { static constexpr int QK = 256, BS = 56;  };
+template <int TYPE> constexpr bool kIsIqGrid = (TYPE == T_IQ2_XXS || TYPE == T_IQ2_XS || TYPE == T_IQ2_S || TYPE == T_IQ3_XXS ||
+                                                TYPE == T_IQ3_S || TYPE == T_IQ1_S || TYPE == T_IQ1_M);
 
 // ---------------------------------------------------------------- host-side error plumbing (api.cu owns the storage)
 void ggb_set_error(const char *fmt, ...);

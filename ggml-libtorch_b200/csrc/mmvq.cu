@@ -402,6 +402,13 @@ int ggb_mmvq_impl(const void *W, const void *X, void *Y, int type, int xy_dtype,
         case T_Q6_K: return dispatch_dtype<T_Q6_K>(W, X, Y, xy_dtype, B, K, N, stream);
         case T_IQ4_NL: return dispatch_dtype<T_IQ4_NL>(W, X, Y, xy_dtype, B, K, N, stream);
         case T_IQ4_XS: return dispatch_dtype<T_IQ4_XS>(W, X, Y, xy_dtype, B, K, N, stream);
+        case T_IQ2_XXS: return dispatch_dtype<T_IQ2_XXS>(W, X, Y, xy_dtype, B, K, N, stream);
+        case T_IQ2_XS: return dispatch_dtype<T_IQ2_XS>(W, X, Y, xy_dtype, B, K, N, stream);
+        case T_IQ2_S: return dispatch_dtype<T_IQ2_S>(W, X, Y, xy_dtype, B, K, N, stream);
+        case T_IQ3_XXS: return dispatch_dtype<T_IQ3_XXS>(W, X, Y, xy_dtype, B, K, N, stream);
+        case T_IQ3_S: return dispatch_dtype<T_IQ3_S>(W, X, Y, xy_dtype, B, K, N, stream);
+        case T_IQ1_S: return dispatch_dtype<T_IQ1_S>(W, X, Y, xy_dtype, B, K, N, stream);
+        case T_IQ1_M: return dispatch_dtype<T_IQ1_M>(W, X, Y, xy_dtype, B, K, N, stream);
         default:
             ggb_set_error("ggb_mmvq: unsupported ggml type %d", type);
             return GGB_E_TYPE;

@@ -4,6 +4,7 @@
 #pragma once
 
 #include "q8_1.cuh"
+#include "iq_grid.cuh"
 
 namespace ggb_group {
 
@@ -22,6 +23,13 @@ template <> struct VqTraits<T_Q5_K> { static constexpr bool NEED_SQ = true,  NEE
 template <> struct VqTraits<T_Q6_K> { static constexpr bool NEED_SQ = true,  NEED_S8 = false; };
 template <> struct VqTraits<T_IQ4_NL> { static constexpr bool NEED_SQ = false, NEED_S8 = false; };
 template <> struct VqTraits<T_IQ4_XS> { static constexpr bool NEED_SQ = false, NEED_S8 = false; };
+template <> struct VqTraits<T_IQ2_XXS> { static constexpr bool NEED_SQ = false, NEED_S8 = false; };
+template <> struct VqTraits<T_IQ2_XS>  { static constexpr bool NEED_SQ = false, NEED_S8 = false; };
+template <> struct VqTraits<T_IQ2_S>   { static constexpr bool NEED_SQ = false, NEED_S8 = false; };
+template <> struct VqTraits<T_IQ3_XXS> { static constexpr bool NEED_SQ = false, NEED_S8 = false; };
+template <> struct VqTraits<T_IQ3_S>   { static constexpr bool NEED_SQ = false, NEED_S8 = false; };
+template <> struct VqTraits<T_IQ1_S>   { static constexpr bool NEED_SQ = false, NEED_S8 = true;  };   // the shift goes through q8_1's s field
+template <> struct VqTraits<T_IQ1_M>   { static constexpr bool NEED_SQ = false, NEED_S8 = false; };   // the shift is folded into the int8 weights
 
 struct GroupW {
     uint32_t w[8];      // the 32 raw quants of the group, 4 per word, element order
@@ -174,6 +182,51 @@ __device__ __forceinline__ void load_group(const uint8_t *seg, int g, GroupW &o)
         for (int i = 0; i < 4; i++) {
             iq4nl_lut8(ld_u32_a4(b + 8 + 16 * ib + 4 * i), o.w[i], o.w[4 + i]);
         }
+    } else if constexpr (kIsIqGrid<TYPE>) {
+        // codebook formats (iq_grid.cuh; vecdotq.cuh:607-841): four octets of grid values, signs applied, as int8 words.
+        //   IQ2_XXS / IQ3_*: a0 = a1 = (d * (0.5 + ls)) * step          -> combine: (a0 * d8) * dot
+        //   IQ2_XS / IQ2_S:  a0 = 0.5 + ls1, a1 = 0.5 + ls2, m0 = d / 4 -> (m0 * d8) * (a0 * dot0 + a1 * dot1)
+        //   IQ1_S:           weights grid + 1, a0 = d * (2 s + 1), m0 = the shift -1 +- 1/8  -> a0 * (d8 * dot + s8 * m0)
+        //   IQ1_M:           weights 8 * grid +- 1 (exact integers: the reference's sumi + delta * sumy, times 8),
+        //                    a0 = 2 s1 + 1, a1 = 2 s2 + 1, m0 = d / 8   -> (m0 * d8) * (a0 * dot0 + a1 * dot1)
+        const uint8_t *b = seg + (g >> 3) * BS;
+        const int ib = g & 7;
+        const float d = ggb_iq::block_d<TYPE>(b);
+        int ls[4];
+#pragma unroll
+        for (int l = 0; l < 4; l++) {
+            const ggb_iq::Octet oc = ggb_iq::octet<TYPE>(b, ib, l);
+            ls[l] = oc.ls;
+            if constexpr (TYPE == T_IQ1_S) {
+                o.w[2 * l] = oc.lo;
+                o.w[2 * l + 1] = oc.hi;
+                o.m0 = oc.neg_shift ? -1.125f : -0.875f;
+            } else if constexpr (TYPE == T_IQ1_M) {
+                // 8 * (v - 1) +- 1 for v in {0, 1, 2}: bytes 8 v - 9 (shift -1/8) or 8 v - 7 (+1/8), two's complement per byte;
+                // 8 v <= 16 and the subtrahend never borrow across bytes once 0x80 is lent to every byte and taken back
+                const uint32_t sub = oc.neg_shift ? 0x09090909u : 0x07070707u;
+                o.w[2 * l] = (((oc.lo << 3) | 0x80808080u) - sub) ^ 0x80808080u;
+                o.w[2 * l + 1] = (((oc.hi << 3) | 0x80808080u) - sub) ^ 0x80808080u;
+            } else {
+                o.w[2 * l] = ggb_iq::apply_signs4(oc.lo, oc.sign8);
+                o.w[2 * l + 1] = ggb_iq::apply_signs4(oc.hi, oc.sign8 >> 4);
+            }
+        }
+        if constexpr (TYPE == T_IQ2_XXS) {
+            o.a0 = o.a1 = (d * (0.5f + (float)ls[0])) * 0.25f;
+        } else if constexpr (TYPE == T_IQ3_XXS || TYPE == T_IQ3_S) {
+            o.a0 = o.a1 = (d * (0.5f + (float)ls[0])) * 0.5f;
+        } else if constexpr (TYPE == T_IQ2_XS || TYPE == T_IQ2_S) {
+            o.a0 = 0.5f + (float)ls[0];
+            o.a1 = 0.5f + (float)ls[2];
+            o.m0 = d * 0.25f;
+        } else if constexpr (TYPE == T_IQ1_S) {
+            o.a0 = o.a1 = d * (float)ls[0];
+        } else {   // T_IQ1_M
+            o.a0 = (float)ls[0];
+            o.a1 = (float)ls[2];
+            o.m0 = d * 0.125f;
+        }
     } else {   // T_Q6_K
         const uint8_t *b = seg + (g >> 3) * BS;
         const int j = g & 7, ip = j >> 2, r = j & 3;
@@ -205,8 +258,13 @@ __device__ __forceinline__ float combine(const GroupW &g, int dot0, int dot1, fl
         const float d4d8 = __half2float(__float2half_rn(g.a0 * d8));      // __hmul2(dm, ds8) in half
         const float m4s8 = __half2float(__float2half_rn(g.m0 * s8));
         return (float)(dot0 + dot1) * d4d8 + m4s8;
-    } else if constexpr (TYPE == T_Q8_0 || TYPE == T_IQ4_NL || TYPE == T_IQ4_XS) {      // vecdotq.cuh:842-888 for the two IQ4
+    } else if constexpr (TYPE == T_Q8_0 || TYPE == T_IQ4_NL || TYPE == T_IQ4_XS || TYPE == T_IQ2_XXS || TYPE == T_IQ3_XXS ||
+                         TYPE == T_IQ3_S) {                                           // vecdotq.cuh:842-888 for the two IQ4
         return (g.a0 * d8) * (float)(dot0 + dot1);
+    } else if constexpr (TYPE == T_IQ2_XS || TYPE == T_IQ2_S || TYPE == T_IQ1_M) {    // vecdotq.cuh:631-704, 797-841
+        return (g.m0 * d8) * (g.a0 * (float)dot0 + g.a1 * (float)dot1);
+    } else if constexpr (TYPE == T_IQ1_S) {                                          // vecdotq.cuh:762-795
+        return g.a0 * (d8 * (float)(dot0 + dot1) + __uint_as_float(aux) * g.m0);
     } else {
         const int sq0 = (int)(int16_t)(aux & 0xffffu), sq1 = (int)(int16_t)(aux >> 16);
         if constexpr (TYPE == T_Q2_K) {

@@ -673,7 +673,12 @@ bool plan(MmaParams &p, int &smem, int NW, int cs, int P, int B, int K, int64_t 
     const ActLayout L = act_layout(B, K / P, Ops::S16);
     const int pc = p.nchunks / P;
     int sl = 0;
-    while ((2 << sl) <= pc && (2 << sl) <= NW) sl++;             // S = largest power of two <= min(chunks per phase, NW)
+    // S = warps per team, a power of two <= min(chunks per phase, NW), chosen from K alone (the summation order must not
+    // depend on N or the grid).  Measured, Q4_K batch 4 / 8 (profiles/r02_mmvq_mma_teams.log): teams of 2 win on K <= 8192
+    // (14336 x 4096: 14.5 / 14.8 -> 12.7 / 13.4 us, 28672 x 8192: 36.0 / 40.8 -> 31.3 / 35.5) -- fewer partial-sum barriers,
+    // more row groups in flight --, teams of 4 on longer rows (4096 x 14336: 14.4 -> 13.7 at batch 8, 8192 x 28672: 47.2 -> 44.2)
+    const int sl_cap = K <= 8192 ? 1 : 2;
+    while (sl < sl_cap && (2 << sl) <= pc && (2 << sl) <= NW) sl++;
     if (g_s_log2 >= 0 && (1 << g_s_log2) <= pc && (1 << g_s_log2) <= NW) sl = g_s_log2;
     p.s_log2 = sl;
     p.slot_row_stride = rs;

@@ -1,4 +1,4 @@
-// mmvq_rg.cu -- batch-1 MMVQ with the q8_1 activations RESIDENT IN REGISTERS (Q4_K; K % 256 == 0, K <= 16384).
+// mmvq_rg.cu -- batch-1 MMVQ with the q8_1 activations RESIDENT IN REGISTERS (Q4_K; K % 256 == 0, K <= 16384, 24576, 28672).
 //
 // Same contract as the other MMVQ kernels (ggml_mul_mat_vec_a8 = quantize_row_q8_1_cuda + mul_mat_vec_q + vec_dot_q4_K_q8_1,
 // hf-kernels/ggml-kernels/ggml/ggml_kernel.cu:13-66,80-193; ggml/mmvq.cuh:2-38; ggml/vecdotq.cuh:266-327).
@@ -32,7 +32,8 @@ unsigned long long *ggb_mmvq_trace_slot();
 
 namespace {
 
-constexpr int kNW = 12;                  // warps per CTA
+// warps per CTA: 12 (rows of 1, 2, 3, 4 or 6 chunks), or 14 for the seven chunks of K = 28672 (the 70B down projection; 72 registers,
+// no spills)
 constexpr int kDefaultCluster = 2;       // CTAs sharing one activation quantization (measured)
 constexpr int kChunkItems = 32;          // items (128 values) per row chunk = one per lane
 
@@ -44,7 +45,7 @@ struct RgParams {
     int64_t N;
     int K, nsb, ipr, row_bytes;
     int C;               // chunks per row
-    int RW;              // row lanes per CTA = kNW / C
+    int RW;              // row lanes per CTA = NW / C
     int off_scales, off_part, off_bar, off_slots;
     int spc;             // super-blocks per chunk
     int early;           // rows per warp requested before the dependency wait (static weights), 1..kStages
@@ -180,8 +181,8 @@ __device__ __forceinline__ long long clk64() {
 // S = row chunks in flight per warp (ring stages): 4 where the ring fits beside the activations in half an SM's shared
 // memory (K = 4096: 12 warps x 4 x 2304 B + 5 KB = exactly the 113 KB two resident CTAs may have each), else 3.
 // FULL = every chunk has 16 super-blocks (K % 4096 == 0): all lanes own an item and the copy needs no bounds.
-template <int TYPE, typename T, int S, bool FULL>
-__global__ void __launch_bounds__(kNW * 32, 2)
+template <int TYPE, typename T, int S, bool FULL, int NW>
+__global__ void __launch_bounds__(NW * 32, 2)
 mmvq_rg_kernel(const RgParams p) {
     using Ops = RgOps<TYPE>;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -198,7 +199,12 @@ mmvq_rg_kernel(const RgParams p) {
     const int nrows = (int)(r_end - r_begin);
 
     unsigned long long *tr = p.trace ? p.trace + blockIdx.x * 8 : nullptr;
-    if (tr && tid == 0) { tr[7] = gtime(); tr[0] = clk64(); }
+    if (tr && tid == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        tr[7] = (gtime() & ~0xffULL) | smid;                          // (the SM in the low byte: which CTAs share one)
+        tr[0] = clk64();
+    }
     ggb_pdl_launch_dependents();
     // Cluster of CL CTAs (launch attribute; CL = 1: none): each CTA quantizes 1 / CL of the activation row and writes its part
     // into every CTA's shared memory (DSMEM), so the row is read from L2 and quantized CL times less often per SM.  The
@@ -278,7 +284,7 @@ mmvq_rg_kernel(const RgParams p) {
     const int g_share = (ngroups_all + (int)CL - 1) / (int)CL;
     const int g_first = (int)crank * g_share, ngroups_row = min(ngroups_all, g_first + g_share);
     const uint32_t act_q_s = smem_u32(act_q), act_s_s = smem_u32(act_s);
-    constexpr int GPI = (kNW * 32) / 4;
+    constexpr int GPI = (NW * 32) / 4;
     auto quantize_pass = [&](auto u_tag, int base, bool first) {
         constexpr int U = decltype(u_tag)::value;
         const int t4 = lane & 3;
@@ -441,7 +447,7 @@ mmvq_rg_kernel(const RgParams p) {
     cp_async_wait<0>();
     if (C > 1) {
         __syncthreads();
-        for (int lr = tid; lr < nrows; lr += kNW * 32) {
+        for (int lr = tid; lr < nrows; lr += NW * 32) {
             float s = part_sm[lr * C];
             for (int cc = 1; cc < C; cc++) s += part_sm[lr * C + cc];
             ggb_yout_store<T>(p.yo, 0, r_begin + lr, s);
@@ -450,29 +456,36 @@ mmvq_rg_kernel(const RgParams p) {
     if (tr && tid == 0) tr[6] = clk64();
 }
 
-template <int TYPE, typename T, int S, bool FULL>
+template <int TYPE, typename T, int S, bool FULL, int NW>
 int launch_cfg(RgParams &p, int grid, int smem, int cluster, cudaStream_t stream) {
     const DeviceInfo &di = ggb_device_info();
     static bool attr_set[64] = {};               // per instantiation and device; idempotent, so a race is harmless
     if (!attr_set[di.dev]) {
-        GGB_CUDA_TRY(cudaFuncSetAttribute(mmvq_rg_kernel<TYPE, T, S, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin));
+        GGB_CUDA_TRY(cudaFuncSetAttribute(mmvq_rg_kernel<TYPE, T, S, FULL, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin));
         attr_set[di.dev] = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kNW * 32);
+    cfg.blockDim = dim3(NW * 32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[2];
+    cudaLaunchAttribute attr[3];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     attr[1].id = cudaLaunchAttributeClusterDimension;
     attr[1].val.clusterDim.x = (unsigned)cluster;
     attr[1].val.clusterDim.y = 1;
     attr[1].val.clusterDim.z = 1;
+    // the two CTAs of a cluster on DIFFERENT SMs: with room for two CTAs per SM the default policy may put a pair on one SM,
+    // which leaves another SM without a CTA of this launch (measured in the 70B block, gate|up -> down -> gate|up: the CTAs of
+    // one launch ended up to 13 us apart; profiles/r02_block_trace.log)
+    attr[2].id = cudaLaunchAttributeClusterSchedulingPolicyPreference;
+    const int pol = (ggb_sb::g_rg_mode >> 24) & 3;
+    attr[2].val.clusterSchedulingPolicyPreference = pol == 1 ? cudaClusterSchedulingPolicyDefault
+                                                   : pol == 2 ? cudaClusterSchedulingPolicyLoadBalancing : cudaClusterSchedulingPolicySpread;
     cfg.attrs = attr;
-    cfg.numAttrs = cluster > 1 ? 2 : 1;
-    GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmvq_rg_kernel<TYPE, T, S, FULL>, p));
+    cfg.numAttrs = cluster > 1 ? 3 : 1;
+    GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmvq_rg_kernel<TYPE, T, S, FULL, NW>, p));
     return GGB_OK;
 }
 
@@ -492,9 +505,11 @@ int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, const vo
     p.ipr = 2 * p.nsb;
     p.row_bytes = p.nsb * Ops::BS;
     p.C = (p.nsb + 15) / 16;
-    if (p.C > 4 || kNW % p.C != 0 || p.row_bytes % 16 != 0) return 1;
+    const int nw = (p.C == 7) ? 14 : 12;
+    const bool full = p.nsb % 16 == 0;
+    if (p.C > 7 || nw % p.C != 0 || p.row_bytes % 16 != 0 || (nw == 14 && !full)) return 1;
     p.spc = (p.nsb + p.C - 1) / p.C;
-    p.RW = kNW / p.C;
+    p.RW = nw / p.C;
     p.wstep = (long long)p.RW * p.row_bytes;
     p.x_vec = (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.xin.x2) & 15) == 0 &&
               (p.xin.ldx * (int64_t)sizeof(T)) % 16 == 0;
@@ -511,23 +526,28 @@ int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, const vo
     if (grid > di.sm_count) grid -= cluster;
     p.part_rows = p.C > 1 ? (int)((N + grid - 1) / grid + 1) : 0;
     if ((int64_t)p.part_rows * p.C * 4 > 16384) return 1;
-    p.off_scales = ((int)K + 15) & ~15;
-    p.off_part = p.off_scales + 2 * p.ipr * 16;
+    p.off_scales = ((int)K + 15) & ~15;                     // (also the scale table's offset inside a pre-launched image)
+    // a pre-launched image is read straight into registers: no activation area in shared memory, the ring gets the room
+    p.off_part = image != nullptr ? 0 : p.off_scales + 2 * p.ipr * 16;
     p.off_bar = (p.off_part + p.part_rows * p.C * 4 + 7) & ~7;                // (only a cluster launch uses it)
     p.off_slots = (p.off_bar + (cluster > 1 ? 8 : 0) + 127) & ~127;
     const int half_sm = (di.max_smem_optin + 1024) / 2 - 1024;               // two CTAs per SM
-    const bool full = p.nsb % 16 == 0;
     const int force_s = (ggb_sb::g_rg_mode >> 12) & 0xf;                     // debug: 3 or 4 stages
     constexpr int stage_bytes = 16 * Ops::BS;
-    int S = (p.off_slots + kNW * 4 * stage_bytes <= half_sm) ? 4 : 3;
-    if (force_s == 3) S = 3;
-    const int smem = p.off_slots + kNW * S * stage_bytes;
+    int S = 4;
+    while (S > 2 && p.off_slots + nw * S * stage_bytes > half_sm) S--;
+    if (force_s == 3 && S > 3) S = 3;
+    if (nw == 14 && S > 3) S = 3;                                             // (instantiated: 12 warps x {3, 4}, 14 warps x {2, 3})
+    if (nw == 12 && S < 3) return 1;
+    const int smem = p.off_slots + nw * S * stage_bytes;
     if (smem > half_sm) return 1;
     if (probe_only) return 2;
     if (p.early == 0 || p.early > S) p.early = 1;
     p.trace = ggb_mmvq_trace_slot();
-    if (S == 4) return full ? launch_cfg<TYPE, T, 4, true>(p, grid, smem, cluster, stream) : launch_cfg<TYPE, T, 4, false>(p, grid, smem, cluster, stream);
-    return full ? launch_cfg<TYPE, T, 3, true>(p, grid, smem, cluster, stream) : launch_cfg<TYPE, T, 3, false>(p, grid, smem, cluster, stream);
+    if (nw == 14)
+        return S == 3 ? launch_cfg<TYPE, T, 3, true, 14>(p, grid, smem, cluster, stream) : launch_cfg<TYPE, T, 2, true, 14>(p, grid, smem, cluster, stream);
+    if (S == 4) return full ? launch_cfg<TYPE, T, 4, true, 12>(p, grid, smem, cluster, stream) : launch_cfg<TYPE, T, 4, false, 12>(p, grid, smem, cluster, stream);
+    return full ? launch_cfg<TYPE, T, 3, true, 12>(p, grid, smem, cluster, stream) : launch_cfg<TYPE, T, 3, false, 12>(p, grid, smem, cluster, stream);
 }
 
 template <int TYPE>
@@ -549,7 +569,7 @@ void ggb_mmvq_rg_set_mode(int mode) { ggb_sb::g_rg_mode = mode; }
 // probe_only: 2 = it applies (nothing launched)
 int ggb_mmvq_rg_impl(const void *W, const void *X, void *Y, int type, int xy_dtype, int64_t B, int64_t K, int64_t N,
                      const void *image, int probe_only, cudaStream_t stream) {
-    if (!(ggb_sb::g_rg_mode & 1) || B != 1 || K % 256 != 0 || K > 16384 || (reinterpret_cast<uintptr_t>(W) & 15)) return 1;
+    if (!(ggb_sb::g_rg_mode & 1) || B != 1 || K % 256 != 0 || K > 28672 || (reinterpret_cast<uintptr_t>(W) & 15)) return 1;
     switch (type) {
         case T_Q4_K: return dispatch_dtype<T_Q4_K>(W, X, Y, xy_dtype, K, N, image, probe_only, stream);
         default: return 1;

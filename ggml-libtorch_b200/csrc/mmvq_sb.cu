@@ -56,6 +56,9 @@ GGB_SB_RUN(ggb_mmvq_sb_run_iq4xs);
 // mmvq_rg.cu: batch 1 with register-resident activations (returns 1 when it does not apply; 2 = applies, launch it)
 int ggb_mmvq_rg_impl(const void *W, const void *X, void *Y, int type, int xy_dtype, int64_t B, int64_t K, int64_t N,
                      const void *image, int probe_only, cudaStream_t stream);
+int ggb_mmvq_rgx_impl(const void *W, const void *X, void *Y, int type, int xy_dtype, int64_t B, int64_t K, int64_t N,
+                      cudaStream_t stream);
+namespace ggb_sb { extern int g_rg_mode; }
 int ggb_mmvq_sb_prequant_q4k_b1(const void *X, int xy_dtype, int64_t K, void *image, cudaStream_t stream);
 
 // bytes of the pre-launched activation image ggb_mmvq_sb_impl would use for (type, B, K); 0 = it quantizes in-kernel
@@ -85,6 +88,10 @@ int ggb_mmvq_sb_impl(const void *W, const void *X, void *Y, int type, int xy_dty
             image = ws;
         }
         return ggb_mmvq_rg_impl(W, X, Y, type, xy_dtype, B, K, N, image, 0, stream);
+    }
+    if ((g_rg_mode & 2) && B == 1) {             // debug: the generic register-resident kernel for Q5_K / Q6_K / IQ4_XS too
+        const int rc = ggb_mmvq_rgx_impl(W, X, Y, type, xy_dtype, B, K, N, stream);
+        if (rc != 1) return rc;
     }
     switch (type) {
         case T_Q4_K: return ggb_mmvq_sb_run_q4k(W, X, Y, xy_dtype, B, K, N, ws, ws_bytes, stream);

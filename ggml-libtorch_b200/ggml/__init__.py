@@ -33,8 +33,9 @@ _DT = {torch.float32: GGB_F32, torch.float16: GGB_F16, torch.bfloat16: GGB_BF16}
 _DT_INV = {v: k for k, v in _DT.items()}
 
 # ggml_type ids, ggml/ggml-common.h:1128-1161
-SUPPORTED_TYPES = (2, 3, 6, 7, 8, 10, 11, 12, 13, 14, 20, 23)
-MMQ_TYPES = (2, 3, 6, 7, 8, 10, 11, 12, 13, 14)      # IQ4_NL (20) / IQ4_XS (23): dequantize + MMVQ only, as in the reference
+SUPPORTED_TYPES = (2, 3, 6, 7, 8, 10, 11, 12, 13, 14, 20, 23, 16, 17, 18, 19, 21, 22, 29)
+MMQ_TYPES = (2, 3, 6, 7, 8, 10, 11, 12, 13, 14)      # the IQ types (IQ4_NL 20, IQ4_XS 23, IQ2_XXS 16, IQ2_XS 17, IQ3_XXS 18, IQ1_S 19,
+                                                      # IQ3_S 21, IQ2_S 22, IQ1_M 29): dequantize + MMVQ only, as in the reference
 MMVQ_MAX_BATCH = 8
 
 

@@ -15,9 +15,11 @@
  *   - return value 0 = enqueued; negative = GGB_E_* and ggb_last_error() (thread-local) says why.
  *     Nothing throws or exits across the ABI (the reference printf+exit()s, ggml/cuda_utils.h:19-27).
  *   - `type` is a ggml_type id (ggml/ggml-common.h:1128-1161): Q4_0=2 Q4_1=3 Q5_0=6 Q5_1=7 Q8_0=8
- *     Q2_K=10 Q3_K=11 Q4_K=12 Q5_K=13 Q6_K=14; IQ4_NL=20 IQ4_XS=23 for ggb_dequantize and ggb_mmvq only (the
- *     coverage the reference has for them: ggml/dequantize.cuh:400-433, ggml/vecdotq.cuh:842-888; ggb_mmq returns
- *     GGB_E_TYPE where the reference's switch, ggml/mmq.cu:222-252, falls through and leaves Y uninitialised).
+ *     Q2_K=10 Q3_K=11 Q4_K=12 Q5_K=13 Q6_K=14; the IQ family -- IQ2_XXS=16 IQ2_XS=17 IQ3_XXS=18 IQ1_S=19 IQ4_NL=20
+ *     IQ3_S=21 IQ2_S=22 IQ4_XS=23 IQ1_M=29 -- for ggb_dequantize and ggb_mmvq only (the coverage the reference has
+ *     for them: ggml/dequantize.cuh:256-433, ggml/vecdotq.cuh:607-888; ggb_mmq returns GGB_E_TYPE where the
+ *     reference's switch, ggml/mmq.cu:222-252, falls through and leaves Y uninitialised).  IQ3_S uses the
+ *     reference's codebook (ggml-common.h:685, top level 62), not the later ggml one.
  *   - dtype codes: GGB_F32=0, GGB_F16=1, GGB_BF16=2.
  */
 #ifndef GGML_B200_H

@@ -20,14 +20,17 @@ _REF_PATH = os.path.join(_HERE, "_ref", "custom_ops.so")
 Q4_0, Q4_1, Q5_0, Q5_1, Q8_0, Q8_1 = 2, 3, 6, 7, 8, 9
 Q2_K, Q3_K, Q4_K, Q5_K, Q6_K = 10, 11, 12, 13, 14
 IQ4_NL, IQ4_XS = 20, 23
+IQ2_XXS, IQ2_XS, IQ3_XXS, IQ1_S, IQ3_S, IQ2_S, IQ1_M = 16, 17, 18, 19, 21, 22, 29
 LEGACY_TYPES = (Q4_0, Q4_1, Q5_0, Q5_1, Q8_0)
 K_TYPES = (Q2_K, Q3_K, Q4_K, Q5_K, Q6_K)
 ALL_TYPES = LEGACY_TYPES + K_TYPES           # dequantize + MMVQ + MMQ
-IQ_TYPES = (IQ4_NL, IQ4_XS)                  # dequantize + MMVQ only (the reference has no MMQ for them either)
+IQ_GRID_TYPES = (IQ2_XXS, IQ2_XS, IQ2_S, IQ3_XXS, IQ3_S, IQ1_S, IQ1_M)    # codebook formats (tables: iq_tables.h)
+IQ_TYPES = (IQ4_NL, IQ4_XS) + IQ_GRID_TYPES  # dequantize + MMVQ only (the reference has no MMQ for them either)
 VEC_TYPES = ALL_TYPES + IQ_TYPES
 BLOCK32_TYPES = LEGACY_TYPES + (IQ4_NL,)     # 32-value blocks: K only needs to be a multiple of 32
 TYPE_NAMES = {2: "Q4_0", 3: "Q4_1", 6: "Q5_0", 7: "Q5_1", 8: "Q8_0", 9: "Q8_1",
-              10: "Q2_K", 11: "Q3_K", 12: "Q4_K", 13: "Q5_K", 14: "Q6_K", 20: "IQ4_NL", 23: "IQ4_XS"}
+              10: "Q2_K", 11: "Q3_K", 12: "Q4_K", 13: "Q5_K", 14: "Q6_K", 20: "IQ4_NL", 23: "IQ4_XS",
+              16: "IQ2_XXS", 17: "IQ2_XS", 18: "IQ3_XXS", 19: "IQ1_S", 21: "IQ3_S", 22: "IQ2_S", 29: "IQ1_M"}
 
 
 def build(force: bool = False) -> str:
@@ -249,8 +252,13 @@ def random_weights(qtype: int, rows: int, cols: int, seed: int = 0) -> np.ndarra
     blocks = rng.integers(0, 256, size=(nb, bs), dtype=np.uint8)
     half_offsets = {Q4_0: [0], Q4_1: [0, 2], Q5_0: [0], Q5_1: [0, 2], Q8_0: [0],
                     Q2_K: [80, 82], Q3_K: [108], Q4_K: [0, 2], Q5_K: [0, 2], Q6_K: [208],
-                    IQ4_NL: [0], IQ4_XS: [0]}[qtype]
+                    IQ4_NL: [0], IQ4_XS: [0], IQ2_XXS: [0], IQ2_XS: [0], IQ2_S: [0], IQ3_XXS: [0], IQ3_S: [0], IQ1_S: [0],
+                    IQ1_M: []}[qtype]
     for off in half_offsets:
         h = (rng.uniform(0.5, 1.5, size=nb) * 2.0 ** -10).astype(np.float16)
         blocks[:, off:off + 2] = h.view(np.uint8).reshape(nb, 2)
+    if qtype == IQ1_M:      # its fp16 scale lives in the top nibbles of the four 16-bit scale words (bytes 49, 51, 53, 55)
+        h = (rng.uniform(0.5, 1.5, size=nb) * 2.0 ** -10).astype(np.float16).view(np.uint16)
+        for i in range(4):
+            blocks[:, 49 + 2 * i] = (blocks[:, 49 + 2 * i] & 0x0f) | (((h >> (4 * i)) & 0x0f) << 4).astype(np.uint8)
     return blocks.reshape(rows, cols // qk * bs)

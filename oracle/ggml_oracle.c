@@ -15,6 +15,12 @@
  *     block_iq4_xs), element layout ggml/dequantize.cuh:400-433, the 16-entry codebook kvalues_iq4nl
  *     (ggml-common.h:1060), fp32 operation order of gguf-py quants.py (classes IQ4_NL, IQ4_XS); MMVQ math
  *     ggml/vecdotq.cuh:842-888.  The reference has no MMQ for these two types and neither has orc_mmq.
+ *   - IQ2_XXS / IQ2_XS / IQ2_S / IQ3_XXS / IQ3_S / IQ1_S / IQ1_M (rest of SURVEY.md section 8f rank 3): block structs
+ *     ggml/ggml-common.h:110-168, dequantize ggml/dequantize.cuh:256-399 (fp32 operation order, identical to gguf-py's
+ *     classes of the same names), MMVQ math ggml/vecdotq.cuh:607-841.  The codebooks (iq_tables.h) are GENERATED from
+ *     gguf-py by scripts/gen_iq_tables.py and were compared there with the reference's tables (ggml-common.h:193-1057).
+ *     IQ3_S follows the REFERENCE (grid levels 4..52, 62 with d * (0.5 + ls) * 0.5), which differs from today's gguf-py
+ *     (levels 1..13, 15 with d * (1 + 2 ls)) on the top level only: 15.5 vs 15.
  *   - q8_1 activation quantization               ggml/ggml_kernel.cu:13-50
  *   - q8_1_mmq activation quantization           ggml/mmq.cu:84-154, ggml/mmq.cuh:176-181
  *   - MMVQ math (integer dots + scale algebra)   ggml/vecdotq.cuh:45-345, 347-605; ggml/mmvq.cuh:2-38
@@ -38,6 +44,7 @@
 #endif
 
 #include "ggml_oracle.h"
+#include "iq_tables.h"
 
 /* ------------------------------------------------------------------ fp16 helpers */
 
@@ -110,6 +117,7 @@ int orc_block_elems(int type) {
         case ORC_Q2_K: case ORC_Q3_K: case ORC_Q4_K: case ORC_Q5_K: case ORC_Q6_K: return 256;
         case ORC_IQ4_NL: return 32;
         case ORC_IQ4_XS: return 256;
+        case ORC_IQ2_XXS: case ORC_IQ2_XS: case ORC_IQ2_S: case ORC_IQ3_XXS: case ORC_IQ3_S: case ORC_IQ1_S: case ORC_IQ1_M: return 256;
         default: return 0;
     }
 }
@@ -121,6 +129,8 @@ int orc_block_bytes(int type) {
         case ORC_Q2_K: return 84;  case ORC_Q3_K: return 110; case ORC_Q4_K: return 144;
         case ORC_Q5_K: return 176; case ORC_Q6_K: return 210;
         case ORC_IQ4_NL: return 18; case ORC_IQ4_XS: return 136;
+        case ORC_IQ2_XXS: return 66; case ORC_IQ2_XS: return 74; case ORC_IQ2_S: return 82;
+        case ORC_IQ3_XXS: return 98; case ORC_IQ3_S: return 110; case ORC_IQ1_S: return 50; case ORC_IQ1_M: return 56;
         default: return 0;
     }
 }
@@ -229,10 +239,174 @@ static void unpack_block_ints(int type, const uint8_t *b, int *q) {
     }
 }
 
+
+/* ------------------------------------------------------------------ IQ1 / IQ2 / IQ3 codebook formats */
+
+static inline int is_iq_grid_type(int type) {
+    return type == ORC_IQ2_XXS || type == ORC_IQ2_XS || type == ORC_IQ2_S || type == ORC_IQ3_XXS || type == ORC_IQ3_S ||
+           type == ORC_IQ1_S || type == ORC_IQ1_M;
+}
+static inline uint32_t ld32(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+/* ksigns_iq2xs (ggml-common.h:1013): the 7-bit index plus an eighth bit that makes the parity even */
+static inline uint32_t ksign8(uint32_t i7) {
+    uint32_t p = i7 ^ (i7 >> 4); p ^= p >> 2; p ^= p >> 1;
+    return i7 | ((p & 1u) << 7);
+}
+
+/* One 32-value group ib (0..7) of a super-block: the integers the reference's vec_dot multiplies with the q8 quants
+ * (IQ2 / IQ3: signed grid values; IQ1: grid + 1 in {0, 1, 2}) and the group's scale parts:
+ *   sc[0], sc[1]  integer sub-scales of elements 0..15 / 16..31 as the reference uses them (ls; IQ1: 2 * s + 1)
+ *   dlt[l]        IQ1: the additive shift of the 8 values l (-1 +- 0.125), else 0 */
+static void iq_group(int type, const uint8_t *b, int ib, int *q, int *sc, float *dlt) {
+    for (int l = 0; l < 4; l++) dlt[l] = 0.0f;
+    switch (type) {
+    case ORC_IQ2_XXS: {                              /* dequantize.cuh:256-273, vecdotq.cuh:607-629 */
+        const uint8_t *q2 = b + 2 + 8 * ib;
+        const uint32_t aux32 = ld32(q2 + 4);
+        sc[0] = sc[1] = (int)(aux32 >> 28);
+        for (int l = 0; l < 4; l++) {
+            const uint64_t g = iq2xxs_grid[q2[l]];
+            const uint32_t sg = ksign8((aux32 >> (7 * l)) & 127);
+            for (int j = 0; j < 8; j++) { int v = (int)((g >> (8 * j)) & 255); q[8 * l + j] = (sg >> j) & 1 ? -v : v; }
+        }
+        break; }
+    case ORC_IQ2_XS: {                               /* dequantize.cuh:275-291, vecdotq.cuh:631-663 */
+        sc[0] = b[66 + ib] & 0x0f; sc[1] = b[66 + ib] >> 4;
+        for (int l = 0; l < 4; l++) {
+            const uint32_t qv = ld16(b + 2 + 2 * (4 * ib + l));
+            const uint64_t g = iq2xs_grid[qv & 511];
+            const uint32_t sg = ksign8(qv >> 9);
+            for (int j = 0; j < 8; j++) { int v = (int)((g >> (8 * j)) & 255); q[8 * l + j] = (sg >> j) & 1 ? -v : v; }
+        }
+        break; }
+    case ORC_IQ2_S: {                                /* dequantize.cuh:293-307, vecdotq.cuh:665-704 */
+        sc[0] = b[74 + ib] & 0x0f; sc[1] = b[74 + ib] >> 4;
+        for (int l = 0; l < 4; l++) {
+            const uint32_t idx = b[2 + 4 * ib + l] | (((uint32_t)b[66 + ib] << (8 - 2 * l)) & 0x300);
+            const uint64_t g = iq2s_grid[idx];
+            const uint32_t sg = b[34 + 4 * ib + l];
+            for (int j = 0; j < 8; j++) { int v = (int)((g >> (8 * j)) & 255); q[8 * l + j] = (sg >> j) & 1 ? -v : v; }
+        }
+        break; }
+    case ORC_IQ3_XXS: {                              /* dequantize.cuh:309-331, vecdotq.cuh:706-732 */
+        const uint8_t *q3 = b + 2 + 8 * ib;
+        const uint32_t aux32 = ld32(b + 66 + 4 * ib);
+        sc[0] = sc[1] = (int)(aux32 >> 28);
+        for (int l = 0; l < 4; l++) {
+            const uint32_t g1 = iq3xxs_grid[q3[2 * l]], g2 = iq3xxs_grid[q3[2 * l + 1]];
+            const uint32_t sg = ksign8((aux32 >> (7 * l)) & 127);
+            for (int j = 0; j < 4; j++) {
+                int v1 = (int)((g1 >> (8 * j)) & 255), v2 = (int)((g2 >> (8 * j)) & 255);
+                q[8 * l + j] = (sg >> j) & 1 ? -v1 : v1;
+                q[8 * l + 4 + j] = (sg >> (4 + j)) & 1 ? -v2 : v2;
+            }
+        }
+        break; }
+    case ORC_IQ3_S: {                                /* dequantize.cuh:333-354, vecdotq.cuh:734-760 */
+        const uint8_t *qs = b + 2 + 8 * ib;
+        const uint32_t qh = b[66 + ib];
+        sc[0] = sc[1] = (b[106 + ib / 2] >> (4 * (ib % 2))) & 0x0f;
+        for (int l = 0; l < 4; l++) {
+            const uint32_t g1 = iq3s_grid[qs[2 * l] | ((qh << (8 - 2 * l)) & 256)];
+            const uint32_t g2 = iq3s_grid[qs[2 * l + 1] | ((qh << (7 - 2 * l)) & 256)];
+            const uint32_t sg = b[74 + 4 * ib + l];
+            for (int j = 0; j < 4; j++) {
+                int v1 = (int)((g1 >> (8 * j)) & 255), v2 = (int)((g2 >> (8 * j)) & 255);
+                q[8 * l + j] = (sg >> j) & 1 ? -v1 : v1;
+                q[8 * l + 4 + j] = (sg >> (4 + j)) & 1 ? -v2 : v2;
+            }
+        }
+        break; }
+    case ORC_IQ1_S: {                                /* dequantize.cuh:356-376, vecdotq.cuh:762-795 */
+        const uint32_t qh = ld16(b + 34 + 2 * ib);
+        sc[0] = sc[1] = 2 * (int)((qh >> 12) & 7) + 1;
+        for (int l = 0; l < 4; l++) {
+            const uint64_t g = iq1s_grid[b[2 + 4 * ib + l] | (((qh >> (3 * l)) & 7) << 8)];
+            dlt[l] = (qh & 0x8000) ? -1.0f - 0.125f : -1.0f + 0.125f;
+            for (int j = 0; j < 8; j++) q[8 * l + j] = (int)((g >> (8 * j)) & 255);
+        }
+        break; }
+    case ORC_IQ1_M: {                                /* dequantize.cuh:378-399, vecdotq.cuh:797-841 */
+        const uint32_t tmp = ld16(b + 48 + 2 * (ib / 2)) >> (6 * (ib % 2));
+        sc[0] = 2 * (int)(tmp & 7) + 1; sc[1] = 2 * (int)((tmp >> 3) & 7) + 1;
+        for (int l = 0; l < 4; l++) {
+            const uint32_t qhl = (uint32_t)b[32 + 2 * ib + l / 2] >> (4 * (l % 2));
+            const uint64_t g = iq1s_grid[b[4 * ib + l] | ((qhl & 7) << 8)];
+            dlt[l] = (qhl & 8) ? -1.0f - 0.125f : -1.0f + 0.125f;
+            for (int j = 0; j < 8; j++) q[8 * l + j] = (int)((g >> (8 * j)) & 255);
+        }
+        break; }
+    default: break;
+    }
+}
+/* the super-block's fp16 scale (IQ1_M: spread over the top nibbles of its four 16-bit scale words) */
+static inline float iq_block_d(int type, const uint8_t *b) {
+    if (type != ORC_IQ1_M) return h2f(ld16(b));
+    const uint32_t s0 = ld16(b + 48), s1 = ld16(b + 50), s2 = ld16(b + 52), s3 = ld16(b + 54);
+    return h2f((uint16_t)((s0 >> 12) | ((s1 >> 8) & 0x00f0) | ((s2 >> 4) & 0x0f00) | (s3 & 0xf000)));
+}
+
+static void iq_dequant_block(int type, const uint8_t *b, float *y) {
+    const float d = iq_block_d(type, b);
+    for (int ib = 0; ib < 8; ib++) {
+        int q[32], sc[2]; float dlt[4];
+        iq_group(type, b, ib, q, sc, dlt);
+        for (int l = 0; l < 4; l++) {
+            const int s = sc[l / 2];
+            float db;
+            if (type == ORC_IQ1_S || type == ORC_IQ1_M) {
+                db = d * (float)s;                                       /* d * (2 s + 1) */
+                for (int j = 0; j < 8; j++) { const float t = (float)q[8 * l + j] + dlt[l]; y[32 * ib + 8 * l + j] = db * t; }
+            } else {
+                db = d * (0.5f + (float)s);
+                db = db * ((type == ORC_IQ3_XXS || type == ORC_IQ3_S) ? 0.5f : 0.25f);
+                /* d * grid * sign: the sign is an exact factor */
+                for (int j = 0; j < 8; j++) {
+                    const int v = q[8 * l + j];
+                    const float t = db * (float)(v < 0 ? -v : v);
+                    y[32 * ib + 8 * l + j] = v < 0 ? -t : t;
+                }
+            }
+        }
+    }
+}
+
+/* one super-block against 256 q8_1 activations (vecdotq.cuh:607-841), double accumulation */
+static double iq_block_dot(int type, const uint8_t *b, const int8_t *a, const float *dd, const float *ss) {
+    const double d = iq_block_d(type, b);
+    double acc = 0.0;
+    for (int ib = 0; ib < 8; ib++) {
+        int q[32], sc[2]; float dlt[4];
+        iq_group(type, b, ib, q, sc, dlt);
+        const int8_t *u = a + 32 * ib;
+        int s0 = 0, s1 = 0;
+        for (int j = 0; j < 16; j++) { s0 += q[j] * u[j]; s1 += q[16 + j] * u[16 + j]; }
+        switch (type) {
+        case ORC_IQ2_XXS: acc += d * (0.5 + sc[0]) * (double)dd[ib] * 0.25 * (s0 + s1); break;
+        case ORC_IQ2_XS: case ORC_IQ2_S:
+            acc += d * (double)dd[ib] * 0.25 * ((0.5 + sc[0]) * s0 + (0.5 + sc[1]) * s1); break;
+        case ORC_IQ3_XXS: case ORC_IQ3_S: acc += d * (0.5 + sc[0]) * (double)dd[ib] * 0.5 * (s0 + s1); break;
+        case ORC_IQ1_S:                              /* d1q * (d8 * sumi + s8 * delta): the shift goes through q8_1's s field */
+            acc += d * sc[0] * ((double)dd[ib] * (s0 + s1) + (double)ss[ib] * (double)dlt[0]); break;
+        case ORC_IQ1_M: {                            /* the shift goes through the integer sums of the quants */
+            double f[2] = {0.0, 0.0};
+            for (int l = 0; l < 4; l++) {
+                int sumy = 0;
+                for (int j = 0; j < 8; j++) sumy += u[8 * l + j];
+                f[l / 2] += (double)dlt[l] * sumy;
+            }
+            acc += d * (double)dd[ib] * ((s0 + f[0]) * sc[0] + (s1 + f[1]) * sc[1]); break; }
+        default: break;
+        }
+    }
+    return acc;
+}
+
 /* ------------------------------------------------------------------ dequantize */
 
 static void dequant_block(int type, const uint8_t *b, float *y) {
     int q[256];
+    if (is_iq_grid_type(type)) { iq_dequant_block(type, b, y); return; }
     unpack_block_ints(type, b, q);
     switch (type) {
     case ORC_Q4_0: case ORC_Q5_0: {                  /* y = (q - off) * d */
@@ -484,6 +658,7 @@ static double row_dot(int type, const uint8_t *w, int64_t K, const int8_t *q8, c
         const int8_t *a = q8 + ib * qk;
         const float *dd = d8 + ib * (qk / 32);
         const float *ss = s8 + ib * (qk / 32);
+        if (is_iq_grid_type(type)) { acc += iq_block_dot(type, b, a, dd, ss); continue; }
         /* raw (un-offset) quants for the types whose offset is folded through s8 */
         unpack_block_ints(type, b, q);
         switch (type) {
@@ -605,7 +780,7 @@ int orc_mmvq(const void *W, int type, const void *q8_1, int64_t B, int64_t K, in
  * -> Y[M][N] fp32, dst[j*N+i] as mmq.cuh:1764-1790. */
 int orc_mmq(const void *W, int type, const void *q8_1_mmq, int64_t M, int64_t K, int64_t N, float *Y) {
     const int qk = orc_block_elems(type), bs = orc_block_bytes(type);
-    if (qk == 0 || type == ORC_Q8_1 || type == ORC_IQ4_NL || type == ORC_IQ4_XS) return -1;   /* mmq.cu:222-252: no IQ case */
+    if (qk == 0 || type == ORC_Q8_1 || type == ORC_IQ4_NL || type == ORC_IQ4_XS || is_iq_grid_type(type)) return -1;   /* mmq.cu:222-252: no IQ case */
     if (K % qk) return -2;
     const int need_sum = orc_mmq_need_sum(type);
     const int64_t Kp = K - K % 512 + 512, ng = Kp / 32;

@@ -14,7 +14,8 @@ extern "C" {
 enum {
     ORC_Q4_0 = 2, ORC_Q4_1 = 3, ORC_Q5_0 = 6, ORC_Q5_1 = 7, ORC_Q8_0 = 8, ORC_Q8_1 = 9,
     ORC_Q2_K = 10, ORC_Q3_K = 11, ORC_Q4_K = 12, ORC_Q5_K = 13, ORC_Q6_K = 14,
-    ORC_IQ4_NL = 20, ORC_IQ4_XS = 23
+    ORC_IQ4_NL = 20, ORC_IQ4_XS = 23,
+    ORC_IQ2_XXS = 16, ORC_IQ2_XS = 17, ORC_IQ3_XXS = 18, ORC_IQ1_S = 19, ORC_IQ3_S = 21, ORC_IQ2_S = 22, ORC_IQ1_M = 29
 };
 
 int     orc_block_elems(int type);

@@ -35,7 +35,9 @@ rg = int(opt.get("rg", "1")) & 1
 if rg and B == 1 and t == 12:
     # rg kernel: 8 stamps per CTA: clock64 at start, dep-wait done, first X loads landed, quantized, activations in registers,
     # first 4 rows done, end; [7] = globaltimer at start
-    tr = raw.reshape(nl, 256, 8)[:, :148].astype(np.float64)
+    tr = raw.reshape(nl, 256, 8)[:, :148]
+    tr[:, :, 7] &= ~0xff
+    tr = tr.astype(np.float64)
     g0 = tr[0, :, 7].min()
     print(f"rg={opt.get('rg')} static={static} N={N} K={K} B={B}: per-CTA phases in SM cycles (min / median / max over CTAs); start = globaltimer us")
     names = ["start->dep-wait done", "->X loads landed", "->quantized", "->acts in regs", "->first 4 rows", "->end"]

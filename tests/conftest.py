@@ -15,6 +15,9 @@ for p in (ROOT, os.path.join(ROOT, "ggml-libtorch_b200")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from util import patch_gguf_iq3s_to_reference_table
+    patch_gguf_iq3s_to_reference_table()          # IQ3_S: gguf-py follows the reference's codebook (see the helper)
 
 
 def pytest_collection_modifyitems(config, items):

@@ -37,10 +37,11 @@ def test_version_and_geometry(capi):
     assert L.ggb_version() == 100
     want = {2: (32, 18), 3: (32, 20), 6: (32, 22), 7: (32, 24), 8: (32, 34),
             10: (256, 84), 11: (256, 110), 12: (256, 144), 13: (256, 176), 14: (256, 210),
-            20: (32, 18), 23: (256, 136)}
+            20: (32, 18), 23: (256, 136),
+            16: (256, 66), 17: (256, 74), 18: (256, 98), 19: (256, 50), 21: (256, 110), 22: (256, 82), 29: (256, 56)}
     for t, (qk, bs) in want.items():
         assert L.ggb_block_elems(t) == qk and L.ggb_block_bytes(t) == bs
-    for t in (0, 1, 9, 15, 16, 99, -1):
+    for t in (0, 1, 9, 15, 24, 28, 30, 99, -1):
         assert L.ggb_block_elems(t) == 0 and L.ggb_block_bytes(t) == 0
 
 
@@ -127,14 +128,14 @@ def test_fused_supported_query(capi):
 
 
 def test_iq4_types_and_options_without_gpu(capi):
-    """IQ4_NL / IQ4_XS: geometry known, MMQ refused (like the reference, which has no MMQ case for them); every tuning
+    """The IQ types: geometry known, MMQ refused (like the reference, which has no MMQ case for them); every tuning
     option is accepted and restored, an unknown one is an argument error."""
     L = capi.lib
     assert (L.ggb_block_elems(20), L.ggb_block_bytes(20)) == (32, 18)
     assert (L.ggb_block_elems(23), L.ggb_block_bytes(23)) == (256, 136)
     buf = ctypes.create_string_buffer(8192)
     p16 = (ctypes.addressof(buf) + 255) & ~255
-    for t in (20, 23):
+    for t in (20, 23, 16, 17, 18, 19, 21, 22, 29):
         assert L.ggb_mmq(p16, p16, p16, t, capi.GGB_F16, 4, 256, 8, 8, p16, 1 << 20, None) == -1   # GGB_E_TYPE
         assert b"MMVQ only" in L.ggb_last_error()
         assert L.ggb_mmq_workspace_bytes(t, 4, 256, 8) == 0

@@ -54,15 +54,16 @@ def test_load_whole_and_sharded(tmp_path):
 
 
 def test_unsupported_quant_types_are_not_dropped_silently(tmp_path):
-    """Advisor finding (round 1): a model with IQ2 / IQ3 tensors used to load with layers missing and no error."""
+    """Advisor finding (round 1): a model with tensors of an unserved quantized type (then IQ2 / IQ3; now e.g. the ternary TQ2_0)
+    used to load with layers missing and no error."""
     pytest.importorskip("torch")
     pytest.importorskip("ggml", reason="the package needs libggml_b200.so")
     from ggml.loader import UnsupportedQuantTypes, load_gguf
     path = str(tmp_path / "mixed.gguf")
     wr = gguf.GGUFWriter(path, "llama")
     wr.add_tensor("blk.0.ffn_gate_64x256", oracle.random_weights(oracle.Q4_K, 64, 256, seed=1), raw_dtype=gguf.GGMLQuantizationType(12))
-    iq2 = np.zeros((4, 256 // 256 * 66), dtype=np.uint8)                 # IQ2_XXS: 66 bytes per 256 values
-    wr.add_tensor("blk.0.ffn_up_4x256", iq2, raw_dtype=gguf.GGMLQuantizationType.IQ2_XXS)
+    tq2 = np.zeros((4, 256 // 256 * 66), dtype=np.uint8)                 # TQ2_0: 66 bytes per 256 values
+    wr.add_tensor("blk.0.ffn_up_4x256", tq2, raw_dtype=gguf.GGMLQuantizationType.TQ2_0)
     wr.add_tensor("norm.weight", np.ones(256, dtype=np.float32))
     wr.write_header_to_file(); wr.write_kv_data_to_file(); wr.write_tensors_to_file(); wr.close()
     with pytest.raises(UnsupportedQuantTypes, match="ffn_up"):
