@@ -259,6 +259,11 @@ int ggb_mmvq_fused(const void *W, const void *X, const void *X2, int64_t ldx, in
                       (long long)ggb_mmvq_workspace_bytes(type, B, K, N));
         return GGB_E_ARG;
     }
+    if (!ggb_mmvq_fused_supported(type, B, K)) {        // the same verdict as the up-front query, whatever kernels could do it
+        ggb_set_error("ggb_mmvq_fused: type %d with B=%lld, K=%lld is not on the fused path (use ggb_mmvq + an all-gather)",
+                      type, (long long)B, (long long)K);
+        return GGB_E_SHAPE;
+    }
     GgbYOut y = {};
     for (int i = 0; i < n_peers; i++) y.base[i] = y_peers[i];
     y.n = n_peers;
@@ -295,7 +300,7 @@ int ggb_mmvq_fused_supported(int type, int64_t B, int64_t K) {
     if (B < 1 || B > 8 || K <= 0 || K % 256 != 0) return 0;
     switch (type) {
         case T_Q4_K: case T_Q5_K: return 1;
-        case T_IQ4_XS: return (K % 512 == 0 && B <= 4) ? 1 : 0; // 136-byte super-blocks; batches 5-8 run on the generic kernel
+        case T_IQ4_XS: return K % 512 == 0 ? 1 : 0;         // 136-byte super-blocks: rows are 16-byte aligned every 2 of them
         case T_Q6_K: return K % 2048 == 0 ? 1 : 0;          // 210-byte super-blocks: rows are 16-byte aligned every 8 of them
         default: return 0;
     }

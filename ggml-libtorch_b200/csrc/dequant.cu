@@ -132,6 +132,7 @@ int launch_dequant(const void *W, void *out, int64_t nelem, cudaStream_t stream)
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    GGB_CUDA_TRY((ggb_prefer_max_smem_once<dequant_tile_kernel<TYPE, OutT>>(ggb_device_info().dev)));
     GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, dequant_tile_kernel<TYPE, OutT>, static_cast<const uint8_t *>(W),
                                     static_cast<OutT *>(out), nblocks, aligned, ggb_static_weights()));
     return GGB_OK;

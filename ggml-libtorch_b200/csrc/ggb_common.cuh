@@ -62,6 +62,21 @@ const DeviceInfo &ggb_device_info();
 // ggb_set_option(GGB_OPT_STATIC_WEIGHTS): weight tensors are never written by work enqueued shortly before
 int ggb_static_weights();
 
+// Every kernel of the library asks for the LARGEST shared-memory carve-out.  An SM changes its L1 / shared-memory split only while
+// it is idle, so a kernel whose preferred split differs from the running kernel's cannot become resident beside it: under
+// programmatic dependent launch the next kernel then starts only when the SM has drained -- and its CTAs land two per SM on the
+// SMs that drain first (measured with %smid stamps in the 70B block, profiles/r02_block_trace.log: 72 SMs with two CTAs of a
+// launch, 72 with none, and the pattern persists because every launch inherits the slots of the one before the last).
+// Once per kernel instantiation and device; idempotent, so a race between threads is harmless.
+template <auto Kern>                         // (the kernel itself is the template argument: one flag per kernel, not per signature)
+inline cudaError_t ggb_prefer_max_smem_once(int dev) {
+    static bool done[64] = {};
+    if (dev < 0 || dev >= 64 || done[dev]) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(Kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess) done[dev] = true;
+    return e;
+}
+
 // ---------------------------------------------------------------- small device helpers
 __device__ __forceinline__ float ggb_h2f(uint16_t bits) {
     return __half2float(__ushort_as_half(bits));          // exact widening

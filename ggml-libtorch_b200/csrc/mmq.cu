@@ -622,6 +622,8 @@ int launch_quantize(const void *X, int64_t M, int64_t K, uint8_t *img, float *ro
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    GGB_CUDA_TRY((ggb_prefer_max_smem_once<quantize_b_image_kernel<T, true>>(ggb_device_info().dev)));
+    GGB_CUDA_TRY((ggb_prefer_max_smem_once<quantize_b_image_kernel<T, false>>(ggb_device_info().dev)));
     if (d_half) GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, quantize_b_image_kernel<T, true>, x, img, row_scale, M, (int)K, (int)Kp, (int)Mp, vec_ok));
     else        GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, quantize_b_image_kernel<T, false>, x, img, row_scale, M, (int)K, (int)Kp, (int)Mp, vec_ok));
     return GGB_OK;
@@ -732,6 +734,7 @@ int launch_gemm(const void *W, const uint8_t *img, const float *rscale, void *Y,
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 2;
+    GGB_CUDA_TRY((ggb_prefer_max_smem_once<mmq_kernel<TYPE, BN, NB, CL, T, PAIR>>(di.dev)));
     GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmq_kernel<TYPE, BN, NB, CL, T, PAIR>, p, tmap));
     return GGB_OK;
 }

@@ -303,6 +303,7 @@ int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, cudaStre
         attr_set[di.dev] = true;
     }
     const int grid = (int)(N < di.sm_count ? N : di.sm_count);
+    GGB_CUDA_TRY((ggb_prefer_max_smem_once<mmvq_kernel<TYPE, B, T>>(di.dev)));
     mmvq_kernel<TYPE, B, T><<<grid, kThreads, smem, stream>>>(p, tmap);
     GGB_CUDA_TRY(cudaGetLastError());
     return GGB_OK;

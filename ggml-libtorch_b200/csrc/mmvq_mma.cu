@@ -78,6 +78,12 @@ struct MmaParams {
     int row_bytes;
     unsigned long long *trace;   // debug: per-CTA globaltimer stamps {start, dependency resolved, activations in, end}
     int pdl_prefetch;
+    // inline_q != 0: no image launch -- the two CTAs of a cluster quantize half of the B x K activations each and write their
+    // groups into BOTH CTAs' shared-memory image (st.async, bytes counted on the destination's mbarrier)
+    int inline_q;
+    const void *X;
+    GgbXIn xin;
+    int x_vec;
 };
 
 __device__ __forceinline__ uint4 lds128(const void *p) { return *reinterpret_cast<const uint4 *>(p); }
@@ -91,6 +97,24 @@ __device__ __forceinline__ unsigned long long gtime() {
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// thread-block cluster helpers (the pair that shares one activation quantization; same scheme as mmvq_rg.cu)
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t mapa(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_async_v2(uint32_t addr, uint32_t x, uint32_t y, uint32_t mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];"
+                 ::"r"(addr), "r"(x), "r"(y), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void st_async_b32(uint32_t addr, uint32_t x, uint32_t mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+                 ::"r"(addr), "r"(x), "r"(mbar) : "memory");
 }
 
 constexpr int kMagicBits = 0x4B400000;              // 1.5 * 2^23
@@ -119,11 +143,15 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1
 // ------------------------------------------------------------------------------------------------
 // launch 1: the activation image
 // ------------------------------------------------------------------------------------------------
-template <typename T, bool S16>
+// SMODE: what the per-group table at off_s holds -- 0: tf32 {hi, lo} of d8 * sum(q8); 1: the same per 16-value sub-block, times
+// 32 (Q6_K); 2: {s, 0} with s = the fp16-rounded sum of the raw inputs, block_q8_1.s (the legacy types' offsets and minima go
+// through it: vecdotq.cuh:45-162)
+template <typename T, int SMODE>
 __global__ void __launch_bounds__(256)
 mmvq_act_image_kernel(const T *__restrict__ X, const GgbXIn xin, uint8_t *__restrict__ img, int B, int K, int x_vec) {
     pdl_launch_dependents();
     pdl_wait();                                             // X comes from the previous kernel of the stream
+    constexpr bool S16 = SMODE == 1;
     const ActLayout L = act_layout(B, K, S16);
     const int ng = K >> 5;
     const int t4 = threadIdx.x & 3;
@@ -138,7 +166,7 @@ mmvq_act_image_kernel(const T *__restrict__ X, const GgbXIn xin, uint8_t *__rest
 #pragma unroll
         for (int i = 0; i < 8; i++) v[i] = 0.0f;            // the missing token of an odd batch: zero scales
     }
-    const Q8Group qg = q8_1_quantize_group<false>(v);
+    const Q8Group qg = q8_1_quantize_group<SMODE == 2>(v);
     int sum = __dp4a((int)qg.q_lo, 0x01010101, __dp4a((int)qg.q_hi, 0x01010101, 0));
     sum += __shfl_xor_sync(0xffffffffu, sum, 1);
     const int sum16 = sum;                                   // this lane pair's 16-value half of the group
@@ -153,6 +181,9 @@ mmvq_act_image_kernel(const T *__restrict__ X, const GgbXIn xin, uint8_t *__rest
                 const float hi = __uint_as_float(__float_as_uint(s8) & 0xffffe000u);
                 reinterpret_cast<float2 *>(img + L.off_s)[b * L.s_stride2 + 2 * g + (t4 >> 1)] = make_float2(hi, s8 - hi);
             }
+        } else if (SMODE == 2) {
+            if (t4 == 0)
+                reinterpret_cast<float2 *>(img + L.off_s)[b * L.s_stride2 + g] = make_float2(__half2float(__float2half_rn(qg.sum)), 0.0f);
         } else if (t4 == 0) {
             const float s8 = d8 * (float)sum;
             const float hi = __uint_as_float(__float_as_uint(s8) & 0xffffe000u);
@@ -257,7 +288,7 @@ __device__ __forceinline__ void k45_step(const uint8_t *r0, const uint8_t *r1, c
 
 template <> struct MmaOps<T_Q4_K> {
     static constexpr int BS = 144;
-    static constexpr bool S16 = false;
+    static constexpr int SMODE = 0;
     __device__ __forceinline__ static void step(const uint8_t *r0, const uint8_t *r1, const uint8_t *ap, const float2 *dp,
                                                 const float2 *sp, int *scr, int q, int t, float (&acc)[4]) {
         k45_step<T_Q4_K>(r0, r1, ap, dp, sp, scr, q, t, acc);
@@ -265,7 +296,7 @@ template <> struct MmaOps<T_Q4_K> {
 };
 template <> struct MmaOps<T_Q5_K> {
     static constexpr int BS = 176;
-    static constexpr bool S16 = false;
+    static constexpr int SMODE = 0;
     __device__ __forceinline__ static void step(const uint8_t *r0, const uint8_t *r1, const uint8_t *ap, const float2 *dp,
                                                 const float2 *sp, int *scr, int q, int t, float (&acc)[4]) {
         k45_step<T_Q5_K>(r0, r1, ap, dp, sp, scr, q, t, acc);
@@ -279,7 +310,7 @@ template <> struct MmaOps<T_Q5_K> {
 // 16+4t..16+4t+3 (high nibbles, a2/a3), and reads the matching activation bytes for B.  No minima, no offset.
 template <> struct MmaOps<T_IQ4_XS> {
     static constexpr int BS = 136;
-    static constexpr bool S16 = false;
+    static constexpr int SMODE = 0;
     __device__ __forceinline__ static float scale_of(uint2 hd, int ib) {
         const int ls = (int)(((hd.y >> (4 * ib)) & 0xfu) | (((hd.x >> (16 + 2 * ib)) & 3u) << 4)) - 32;
         return __int_as_float(ls + kMagicBits) - kMagic;     // exact
@@ -411,7 +442,7 @@ __device__ __forceinline__ void q6_step(const uint8_t *r0, const uint8_t *r1, co
 // 4-byte aligned), its fp16 d is the sub-block scale.  Otherwise IQ4_XS's step.
 template <> struct MmaOps<T_IQ4_NL> {
     static constexpr int BS = 144;
-    static constexpr bool S16 = false;
+    static constexpr int SMODE = 0;
     __device__ __forceinline__ static void step(const uint8_t *r0, const uint8_t *r1, const uint8_t *ap, const float2 *dp,
                                                 const float2 *, int *scr, int q, int t, float (&acc)[4]) {
         float *fscr = reinterpret_cast<float *>(scr);
@@ -453,13 +484,129 @@ template <> struct MmaOps<T_IQ4_NL> {
 
 template <> struct MmaOps<T_Q6_K> {
     static constexpr int BS = 210;
-    static constexpr bool S16 = true;
+    static constexpr int SMODE = 1;
     __device__ __forceinline__ static void step(const uint8_t *r0, const uint8_t *r1, const uint8_t *ap, const float2 *dp,
                                                 const float2 *sp, int *, int, int t, float (&acc)[4]) {
         if ((reinterpret_cast<uintptr_t>(r0) & 2) == 0) q6_step<true>(r0, r1, ap, dp, sp, t, acc);     // warp-uniform
         else q6_step<false>(r0, r1, ap, dp, sp, t, acc);
     }
 };
+
+
+// ---- the legacy 32-value block types (round 2): eight blocks = one 256-value unit of the kernel, like IQ4_NL.  Lane t owns
+// values 4t..4t+3 (a0/a1) and 16+4t..16+4t+3 (a2/a3) of every block and the matching activation bytes.  Offsets and minima
+// go through block_q8_1.s = the fp16 sum of the raw inputs, as in the reference (vecdotq.cuh:45-162): SMODE 2.
+//   Q4_0 / Q5_0:  d * (d8 * sumi - off * s)  ->  sum_g (d d8) sumi  -  off * sum_g d[row, g] s[token, g]; the second sum is a
+//                 16 x 8 x 8 GEMM on the tf32 MMA (d and s are fp16 values: exact tf32 operands), like the minima of Q4_K
+//   Q8_0:         (d d8) sumi
+//   Q4_1 / Q5_1:  sumi * h(d d8) + h(m s) with BOTH products rounded to fp16 -- one HMUL2 of the block's (d, m) pair with the
+//                 token's (d8, s) pair, exactly the reference's __hmul2(dm, ds8) (vecdotq.cuh:69-91, 130-162)
+template <int TYPE>
+struct LegacyMma {
+    static constexpr int BB = BlockTraits<TYPE>::BS;                // bytes per 32-value block
+    static constexpr int BS = 8 * BB;
+    static constexpr int SMODE = 2;
+    static constexpr bool HAS_M = (TYPE == T_Q4_1 || TYPE == T_Q5_1);
+    static constexpr bool FIVE = (TYPE == T_Q5_0 || TYPE == T_Q5_1);
+    static constexpr int QH = HAS_M ? 4 : 2;                        // offset of the fifth bits (Q5_*)
+    static constexpr int QS = (TYPE == T_Q4_0 || TYPE == T_Q8_0) ? 2 : TYPE == T_Q4_1 ? 4 : TYPE == T_Q5_0 ? 6 : 8;
+
+    // word at r + OFF: the block sizes make it 4-byte aligned for every block (Q4_1, Q5_1) or for the odd blocks only
+    template <int IB, int OFF>
+    __device__ __forceinline__ static uint32_t word(const uint8_t *r, int t) {
+        constexpr bool AL = ((IB * BB + OFF) % 4) == 0;
+        return ldw_a2<AL>(r + IB * BB + OFF + 4 * t);
+    }
+    template <int IB>
+    __device__ __forceinline__ static void frag(const uint8_t *r, int t, uint32_t &lo, uint32_t &hi) {
+        if constexpr (TYPE == T_Q8_0) {
+            lo = word<IB, QS>(r, t);
+            hi = word<IB, QS + 16>(r, t);
+        } else {
+            const uint32_t w = word<IB, QS>(r, t);
+            lo = w & 0x0f0f0f0fu;
+            hi = (w >> 4) & 0x0f0f0f0fu;
+            if constexpr (FIVE) {                                   // bit j of qh = fifth bit of value j
+                constexpr bool AL = ((IB * BB + QH) % 4) == 0;
+                const uint32_t qh = ldw_a2<AL>(r + IB * BB + QH);
+                lo |= ((((qh >> (4 * t)) & 0xfu) * 0x00204081u) & 0x01010101u) << 4;
+                hi |= ((((qh >> (16 + 4 * t)) & 0xfu) * 0x00204081u) & 0x01010101u) << 4;
+            }
+        }
+    }
+    template <int IB>
+    __device__ __forceinline__ static void group(const uint8_t *r0, const uint8_t *r1, const uint8_t *ap, const float2 *dp,
+                                                 const float2 *s_p0, const float2 *s_p1, const float (&s0)[8], const float (&s1)[8],
+                                                 int t, float (&fs)[4]) {
+        uint32_t a0, a1, a2, a3;
+        frag<IB>(r0, t, a0, a2);
+        frag<IB>(r1, t, a1, a3);
+        const uint32_t b0 = *reinterpret_cast<const uint32_t *>(ap + 32 * IB + 4 * t);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t *>(ap + 32 * IB + 16 + 4 * t);
+        int c[4];
+        mma_s8(c, a0, a1, a2, a3, b0, b1);
+        float cf[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) cf[i] = __int_as_float(c[i] + kMagicBits) - kMagic;       // |dot| <= 32 * 127 * 128 < 2^22: exact
+        const float2 d8 = dp[IB];
+        if constexpr (HAS_M) {
+            const __half2 dm0 = *reinterpret_cast<const __half2 *>(r0 + IB * BB), dm1 = *reinterpret_cast<const __half2 *>(r1 + IB * BB);
+            const __half2 ta = __floats2half2_rn(d8.x, s_p0[IB].x), tb = __floats2half2_rn(d8.y, s_p1[IB].x);   // (d8, s): fp16 values, exact
+            const float2 p00 = __half22float2(__hmul2(dm0, ta)), p01 = __half22float2(__hmul2(dm0, tb));
+            const float2 p10 = __half22float2(__hmul2(dm1, ta)), p11 = __half22float2(__hmul2(dm1, tb));
+            fs[0] += fmaf(cf[0], p00.x, p00.y);
+            fs[1] += fmaf(cf[1], p01.x, p01.y);
+            fs[2] += fmaf(cf[2], p10.x, p10.y);
+            fs[3] += fmaf(cf[3], p11.x, p11.y);
+        } else {
+            constexpr int si = 2 * (IB & 3) + (IB >> 2);
+            fs[0] = fmaf(cf[0], d8.x * s0[si], fs[0]);
+            fs[1] = fmaf(cf[1], d8.y * s0[si], fs[1]);
+            fs[2] = fmaf(cf[2], d8.x * s1[si], fs[2]);
+            fs[3] = fmaf(cf[3], d8.y * s1[si], fs[3]);
+        }
+    }
+    __device__ __forceinline__ static void step(const uint8_t *r0, const uint8_t *r1, const uint8_t *ap, const float2 *dp,
+                                                const float2 *sp, const float2 *s_p0, const float2 *s_p1, int *scr, int q, int t,
+                                                float (&acc)[4]) {
+        float s0[8], s1[8];
+        float cm[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        if constexpr (!HAS_M) {
+            // lane t fetches d of blocks t, t + 4 of rows q, q + 8: the warp's scratch gives every lane all eight per row, and the
+            // four values are the tf32 A fragment of the offset GEMM
+            const float d0a = ggb_h2f(ld_u16(r0 + BB * t)), d0b = ggb_h2f(ld_u16(r0 + BB * (t + 4)));
+            const float d1a = ggb_h2f(ld_u16(r1 + BB * t)), d1b = ggb_h2f(ld_u16(r1 + BB * (t + 4)));
+            float *fscr = reinterpret_cast<float *>(scr);
+            *reinterpret_cast<float2 *>(fscr + q * 8 + 2 * t) = make_float2(d0a, d0b);
+            *reinterpret_cast<float2 *>(fscr + (q + 8) * 8 + 2 * t) = make_float2(d1a, d1b);
+            if constexpr (TYPE != T_Q8_0)
+                mma_tf32(cm, __float_as_uint(d0a), __float_as_uint(d1a), __float_as_uint(d0b), __float_as_uint(d1b),
+                         __float_as_uint(sp[t].x), __float_as_uint(sp[t + 4].x));
+            __syncwarp();
+            const float4 a = *reinterpret_cast<const float4 *>(fscr + q * 8), b = *reinterpret_cast<const float4 *>(fscr + q * 8 + 4);
+            const float4 c = *reinterpret_cast<const float4 *>(fscr + (q + 8) * 8), d = *reinterpret_cast<const float4 *>(fscr + (q + 8) * 8 + 4);
+            s0[0] = a.x; s0[1] = a.y; s0[2] = a.z; s0[3] = a.w; s0[4] = b.x; s0[5] = b.y; s0[6] = b.z; s0[7] = b.w;
+            s1[0] = c.x; s1[1] = c.y; s1[2] = c.z; s1[3] = c.w; s1[4] = d.x; s1[5] = d.y; s1[6] = d.z; s1[7] = d.w;
+        }
+        float fs[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        group<0>(r0, r1, ap, dp, s_p0, s_p1, s0, s1, t, fs);
+        group<1>(r0, r1, ap, dp, s_p0, s_p1, s0, s1, t, fs);
+        group<2>(r0, r1, ap, dp, s_p0, s_p1, s0, s1, t, fs);
+        group<3>(r0, r1, ap, dp, s_p0, s_p1, s0, s1, t, fs);
+        group<4>(r0, r1, ap, dp, s_p0, s_p1, s0, s1, t, fs);
+        group<5>(r0, r1, ap, dp, s_p0, s_p1, s0, s1, t, fs);
+        group<6>(r0, r1, ap, dp, s_p0, s_p1, s0, s1, t, fs);
+        group<7>(r0, r1, ap, dp, s_p0, s_p1, s0, s1, t, fs);
+        constexpr float off = (TYPE == T_Q4_0) ? 8.0f : (TYPE == T_Q5_0) ? 16.0f : 0.0f;
+#pragma unroll
+        for (int i = 0; i < 4; i++) acc[i] += fs[i] - off * cm[i];
+    }
+};
+template <> struct MmaOps<T_Q4_0> : LegacyMma<T_Q4_0> {};
+template <> struct MmaOps<T_Q4_1> : LegacyMma<T_Q4_1> {};
+template <> struct MmaOps<T_Q5_0> : LegacyMma<T_Q5_0> {};
+template <> struct MmaOps<T_Q5_1> : LegacyMma<T_Q5_1> {};
+template <> struct MmaOps<T_Q8_0> : LegacyMma<T_Q8_0> {};
 
 // ------------------------------------------------------------------------------------------------
 // launch 2: the GEMV
@@ -471,8 +618,8 @@ mmvq_mma_kernel(const MmaParams p, const __grid_constant__ CUtensorMap tmapW) {
     using Ops = MmaOps<TYPE>;
     extern __shared__ __align__(128) uint8_t smem[];
     const int P = PHASED ? p.phases : 1, pc = PHASED ? p.nchunks / P : p.nchunks;   // chunks per phase (P divides nchunks)
-    const ActLayout Lg = act_layout(p.B, p.K, Ops::S16);                        // the image in the workspace
-    const ActLayout L = act_layout(p.B, p.K / P, Ops::S16);                     // one phase of it in shared memory
+    const ActLayout Lg = act_layout(p.B, p.K, (Ops::SMODE == 1));                        // the image in the workspace
+    const ActLayout L = act_layout(p.B, p.K / P, (Ops::SMODE == 1));                     // one phase of it in shared memory
     int *scr_all = reinterpret_cast<int *>(smem + p.off_scr);                   // [NW][2][kScrWords]
     float4 *accy = reinterpret_cast<float4 *>(smem + p.off_accy);               // [team][row group][32] (P > 1)
     float4 *part = reinterpret_cast<float4 *>(smem + p.off_part);               // [2][NW][32]
@@ -494,10 +641,20 @@ mmvq_mma_kernel(const MmaParams p, const __grid_constant__ CUtensorMap tmapW) {
     const int nrg = (int)(g_end - g_begin);
 
     const int nslots = NW * p.depth;
+    const bool inl = !PHASED && p.inline_q != 0;                   // (host: only with P == 1 and an even grid of cluster pairs)
     if (tid < nslots) mbar_init(&full[tid], 1);
-    if (tid == 0) mbar_init(act_full, 1);
+    if (tid == 0) {
+        mbar_init(act_full, 1);
+        if (inl) {
+            fence_mbar_init();
+            // every byte both CTAs will store into THIS CTA's image: quants of the B tokens, d8 of the padded token count, s table
+            const int ng = p.K >> 5, ntok = ((p.B + 1) >> 1) << 1;
+            mbar_expect_tx(act_full, (uint32_t)(p.B * p.K + ntok * ng * 4 + p.B * ng * (Ops::SMODE == 1 ? 16 : 8)));
+        }
+    }
     fence_mbar_init();
     __syncthreads();
+    if (inl) cluster_arrive();         // (nothing in flight yet for the release to wait for; the wait sits before the first remote store)
     pdl_launch_dependents();
     if (p.trace && tid == 0) p.trace[blockIdx.x * 4 + 0] = gtime();
 
@@ -544,7 +701,7 @@ mmvq_mma_kernel(const MmaParams p, const __grid_constant__ CUtensorMap tmapW) {
             return;
         }
         const int Kp = p.K / P, k0 = ph * Kp, g0 = k0 >> 5, ngp = Kp >> 5, npairs = (p.B + 1) >> 1;
-        const int sm = Ops::S16 ? 2 : 1;
+        const int sm = (Ops::SMODE == 1) ? 2 : 1;
         mbar_expect_tx(act_full, (uint32_t)(p.B * Kp + npairs * ngp * 8 + p.B * ngp * sm * 8));
         for (int b = 0; b < p.B; b++)
             bulk_g2s(smem + b * L.act_stride, p.act_img + b * Lg.act_stride + k0, (uint32_t)Kp, act_full);
@@ -555,9 +712,85 @@ mmvq_mma_kernel(const MmaParams p, const __grid_constant__ CUtensorMap tmapW) {
             bulk_g2s(smem + L.off_s + b * L.s_stride2 * 8, p.act_img + Lg.off_s + (b * Lg.s_stride2 + g0 * sm) * 8,
                      (uint32_t)(ngp * sm * 8), act_full);
     };
-    if (warp == NW - 1 && lane == 0) load_image(0);                // (the last warp has the fewest units to prime)
-    if (!p.pdl_prefetch)
-        while (is_k < min(p.depth, my_units)) issue_next();
+    if (inl) {
+        // ---- q8_1-quantize this CTA's half of the (token, group) pairs (bit-identical to quantize_q8_1 / the image kernel) and
+        // store every group into both CTAs of the pair.  Four lanes per group, two groups per thread and pass.
+        const T *X = static_cast<const T *>(p.X);
+        const int ng = p.K >> 5, ntok = ((p.B + 1) >> 1) << 1;
+        const int half = (ntok * ng) >> 1;                          // (ng is a multiple of 8: whole warps stay together)
+        const uint32_t crank = cluster_ctarank();
+        const int g_begin = (int)crank * half, g_end = g_begin + half;
+        const int t4 = lane & 3;
+        constexpr int GPP = NW * 8;                                 // groups per pass
+        const uint32_t img_s = smem_u32(smem), bar_s = smem_u32(act_full);
+        const uint32_t img0 = mapa(img_s, 0), img1 = mapa(img_s, 1), bar0 = mapa(bar_s, 0), bar1 = mapa(bar_s, 1);
+        for (int base = g_begin; base < g_end; base += 2 * GPP) {
+            float v[2][8];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int gi = base + u * GPP + (tid >> 2);
+                const int b = gi / ng, g = gi - b * ng;
+                if (gi < g_end && b < p.B) {
+                    load_act8<T>(X, static_cast<const T *>(p.xin.x2), p.xin.ldx, b, g * 32 + t4 * 8, p.x_vec != 0, v[u]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) v[u][i] = 0.0f;
+                }
+            }
+            if (base == g_begin) {
+                if (!p.pdl_prefetch)
+                    while (is_k < min(p.depth, my_units)) issue_next();
+                cluster_wait();                                     // the peer runs: its shared memory and barrier may be written
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                if (base + u * GPP >= g_end) break;                 // block-uniform
+                const int gi = base + u * GPP + (tid >> 2);
+                if (gi >= g_end) continue;                          // warp-uniform (8 groups per warp, half % 8 == 0)
+                const int b = gi / ng, g = gi - b * ng;
+                const Q8Group qg = q8_1_quantize_group<Ops::SMODE == 2>(v[u]);
+                int sum = __dp4a((int)qg.q_lo, 0x01010101, __dp4a((int)qg.q_hi, 0x01010101, 0));
+                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                const int sum16 = sum;
+                sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                const float d8 = __half2float(__float2half_rn(qg.d));
+                const uint32_t qoff = (uint32_t)(b * L.act_stride + g * 32 + t4 * 8);
+                const uint32_t doff = (uint32_t)(L.off_d + (((b >> 1) * L.d_stride2 + g) * 2 + (b & 1)) * 4);
+                uint32_t soff = 0, sx = 0, sy = 0;
+                bool s_on = false;
+                if (b < p.B) {
+                    if (Ops::SMODE == 1) {
+                        s_on = (t4 & 1) == 0;
+                        const float s8 = d8 * (float)(32 * sum16);
+                        const float hi = __uint_as_float(__float_as_uint(s8) & 0xffffe000u);
+                        sx = __float_as_uint(hi); sy = __float_as_uint(s8 - hi);
+                        soff = (uint32_t)(L.off_s + (b * L.s_stride2 + 2 * g + (t4 >> 1)) * 8);
+                    } else {
+                        s_on = t4 == 0;
+                        soff = (uint32_t)(L.off_s + (b * L.s_stride2 + g) * 8);
+                        if (Ops::SMODE == 2) {
+                            sx = __float_as_uint(__half2float(__float2half_rn(qg.sum)));
+                        } else {
+                            const float s8 = d8 * (float)sum;
+                            const float hi = __uint_as_float(__float_as_uint(s8) & 0xffffe000u);
+                            sx = __float_as_uint(hi); sy = __float_as_uint(s8 - hi);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < 2; r++) {
+                    const uint32_t ib = r ? img1 : img0, mb = r ? bar1 : bar0;
+                    if (b < p.B) st_async_v2(ib + qoff, qg.q_lo, qg.q_hi, mb);
+                    if (t4 == 0) st_async_b32(ib + doff, __float_as_uint(d8), mb);
+                    if (s_on) st_async_v2(ib + soff, sx, sy, mb);
+                }
+            }
+        }
+    } else {
+        if (warp == NW - 1 && lane == 0) load_image(0);            // (the last warp has the fewest units to prime)
+        if (!p.pdl_prefetch)
+            while (is_k < min(p.depth, my_units)) issue_next();
+    }
     mbar_wait(act_full, 0);
     if (p.trace && tid == 0) p.trace[blockIdx.x * 4 + 2] = gtime();
 
@@ -567,6 +800,9 @@ mmvq_mma_kernel(const MmaParams p, const __grid_constant__ CUtensorMap tmapW) {
     const uint8_t *act_tok = smem + qc * L.act_stride;
     const float2 *d_pair = reinterpret_cast<const float2 *>(smem + L.off_d) + tc * L.d_stride2;
     const float2 *s_tok = reinterpret_cast<const float2 *>(smem + L.off_s) + qc * L.s_stride2;
+    // (SMODE 2) the s tables of the two tokens whose outputs this lane holds
+    const float2 *s_pair0 = reinterpret_cast<const float2 *>(smem + L.off_s) + min(2 * tc, p.B - 1) * L.s_stride2;
+    const float2 *s_pair1 = reinterpret_cast<const float2 *>(smem + L.off_s) + min(2 * tc + 1, p.B - 1) * L.s_stride2;
     int *scr = scr_all + warp * (2 * kScrWords);
     int ring = ring_base;
     uint32_t phase = 0;
@@ -594,8 +830,12 @@ mmvq_mma_kernel(const MmaParams p, const __grid_constant__ CUtensorMap tmapW) {
 #pragma unroll 1
             for (int i = 0; i < nsbc; i++) {
                 const int sb = sbl0 + i;
-                Ops::step(r0 + i * Ops::BS, r1 + i * Ops::BS, act_tok + sb * 256, d_pair + sb * 8, s_tok + sb * (Ops::S16 ? 16 : 8),
-                          scr + (step_no & 1) * kScrWords, q, t, acc);
+                if constexpr (Ops::SMODE == 2)
+                    Ops::step(r0 + i * Ops::BS, r1 + i * Ops::BS, act_tok + sb * 256, d_pair + sb * 8, s_tok + sb * 8, s_pair0 + sb * 8,
+                              s_pair1 + sb * 8, scr + (step_no & 1) * kScrWords, q, t, acc);
+                else
+                    Ops::step(r0 + i * Ops::BS, r1 + i * Ops::BS, act_tok + sb * 256, d_pair + sb * 8, s_tok + sb * ((Ops::SMODE == 1) ? 16 : 8),
+                              scr + (step_no & 1) * kScrWords, q, t, acc);
                 step_no++;
             }
             __syncwarp();
@@ -651,6 +891,10 @@ mmvq_mma_kernel(const MmaParams p, const __grid_constant__ CUtensorMap tmapW) {
 // ------------------------------------------------------------------------------------------------
 int g_cs = 0, g_s_log2 = -1;          // tuning overrides (0 / -1 = automatic)
 int g_min_batch = 3;                  // batches below this stay on the dp4a kernels
+int g_inline_max_groups = 256;        // in-kernel pair quantization when a CTA's half of the (token, group) pairs is at most this (0 = never).
+                                      // Measured (profiles/r02_mmvq_mma_inline.log, Q4_K): 14336 x 4096 batch 3 / 4 12.7 -> 12.1 / 12.2 us, but batch 8
+                                      // 13.1 -> 14.0 and every longer row loses (4096 x 14336 batch 8: 13.8 -> 34 us): the pass is a chain of
+                                      // L2 loads, shuffles and remote stores per group, and 512 threads get through 256 groups at best
 
 }  // namespace
 
@@ -670,7 +914,7 @@ bool plan(MmaParams &p, int &smem, int NW, int cs, int P, int B, int K, int64_t 
     p.nchunks = (p.nsb + p.cs - 1) / p.cs;
     if (P > 1 && (p.nsb % p.cs != 0 || p.nchunks % P != 0 || (K / P) % 512 != 0)) return false;
     p.phases = P;
-    const ActLayout L = act_layout(B, K / P, Ops::S16);
+    const ActLayout L = act_layout(B, K / P, (Ops::SMODE == 1));
     const int pc = p.nchunks / P;
     int sl = 0;
     // S = warps per team, a power of two <= min(chunks per phase, NW), chosen from K alone (the summation order must not
@@ -721,11 +965,16 @@ int launch_gemv(MmaParams &p, int smem, const CUtensorMap &tmap, cudaStream_t st
     cfg.blockDim = dim3(NW * 32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 2;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = p.inline_q ? 2 : 1;
+    GGB_CUDA_TRY((ggb_prefer_max_smem_once<mmvq_mma_kernel<TYPE, T, NW, PHASED>>(di.dev)));
     GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmvq_mma_kernel<TYPE, T, NW, PHASED>, p, tmap));
     return GGB_OK;
 }
@@ -765,8 +1014,18 @@ int launch(const void *W, const void *X, void *Y, int64_t B, int64_t K, int64_t 
         const int rc = ggb_make_row_tensor_map(&tmap, W, N, p.row_bytes, kRowsPerGroup, p.slot_row_stride, "ggb_mmvq");
         if (rc != GGB_OK) return rc;
     }
+    const GgbXIn xin0 = ggb_make_xin(K);
+    p.X = X;
+    p.xin = xin0;
+    p.x_vec = (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(xin0.x2) & 15) == 0 &&
+              (xin0.ldx * (int64_t)sizeof(T)) % 16 == 0;
+    // Short activation tiles: no image launch.  The CTA pairs of the GEMV quantize half of the tile each and exchange the halves
+    // through distributed shared memory -- one dependency resolution and one trip through L2 less (measured per-CTA timeline,
+    // profiles/r02_mmvq_mma_trace.log: 4.4 us from the end of the previous GEMV to this one's dependency through the image launch).
+    const int64_t half_groups = ((B + 1) / 2) * 2 * (K / 32) / 2;
+    p.inline_q = (p.phases == 1 && grid_est >= 2 && grid_est % 2 == 0 && g_inline_max_groups > 0 && half_groups <= g_inline_max_groups) ? 1 : 0;
     // launch 1: the activation image
-    {
+    if (!p.inline_q) {
         const int ntok = (int)((B + 1) / 2) * 2;
         const int ngroups = ntok * (int)(K / 32);
         cudaLaunchConfig_t cfg = {};
@@ -782,7 +1041,8 @@ int launch(const void *W, const void *X, void *Y, int64_t B, int64_t K, int64_t 
         const GgbXIn xin = ggb_make_xin(K);
         const int x_vec = (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(xin.x2) & 15) == 0 &&
                           (xin.ldx * (int64_t)sizeof(T)) % 16 == 0;
-        GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmvq_act_image_kernel<T, Ops::S16>, static_cast<const T *>(X), xin, static_cast<uint8_t *>(ws),
+        GGB_CUDA_TRY((ggb_prefer_max_smem_once<mmvq_act_image_kernel<T, Ops::SMODE>>(di.dev)));
+        GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmvq_act_image_kernel<T, Ops::SMODE>, static_cast<const T *>(X), xin, static_cast<uint8_t *>(ws),
                                         (int)B, (int)K, x_vec));
     }
     if (p.phases == 1)
@@ -804,7 +1064,9 @@ bool mma_applies(int type, int64_t B, int64_t K) {
     // measured crossover with the dp4a kernel (Llama-8B shapes): batch 3 for K = 4096, batch 2 for the long rows, where
     // the dp4a kernel's per-CTA activation quantization (3.3 us at K = 14336) costs more than the image kernel's launch
     const int64_t min_b = (g_min_batch == 3 && K > 8192) ? 2 : g_min_batch;
-    return (type == T_Q4_K || type == T_Q5_K || type == T_Q6_K || type == T_IQ4_XS || type == T_IQ4_NL) && B >= min_b && B <= 8 && K % 256 == 0 && K <= (1 << 16);
+    const bool legacy = type == T_Q4_0 || type == T_Q4_1 || type == T_Q5_0 || type == T_Q5_1 || type == T_Q8_0;
+    return (type == T_Q4_K || type == T_Q5_K || type == T_Q6_K || type == T_IQ4_XS || type == T_IQ4_NL || legacy) && B >= min_b && B <= 8 &&
+           K % 256 == 0 && K <= (1 << 16);
 }
 
 }  // namespace
@@ -812,7 +1074,8 @@ bool mma_applies(int type, int64_t B, int64_t K) {
 void ggb_mmvq_mma_tune(int cs, int s_log2_plus1, int min_batch) {
     g_cs = cs;
     g_s_log2 = s_log2_plus1 - 1;
-    if (min_batch > 0) g_min_batch = min_batch;
+    if ((min_batch & 0x7f) > 0) g_min_batch = min_batch & 0x7f;
+    g_inline_max_groups = (min_batch & 0x80) ? 0 : 256;           // bit 7: always the image launch
 }
 
 // workspace for the activation image (0 when this path does not apply)
@@ -833,6 +1096,11 @@ int ggb_mmvq_mma_impl(const void *W, const void *X, void *Y, int type, int xy_dt
         case T_Q6_K: rc = dispatch_dtype<T_Q6_K>(W, X, Y, xy_dtype, B, K, N, ws, stream); break;
         case T_IQ4_XS: rc = dispatch_dtype<T_IQ4_XS>(W, X, Y, xy_dtype, B, K, N, ws, stream); break;
         case T_IQ4_NL: rc = dispatch_dtype<T_IQ4_NL>(W, X, Y, xy_dtype, B, K, N, ws, stream); break;
+        case T_Q4_0: rc = dispatch_dtype<T_Q4_0>(W, X, Y, xy_dtype, B, K, N, ws, stream); break;
+        case T_Q4_1: rc = dispatch_dtype<T_Q4_1>(W, X, Y, xy_dtype, B, K, N, ws, stream); break;
+        case T_Q5_0: rc = dispatch_dtype<T_Q5_0>(W, X, Y, xy_dtype, B, K, N, ws, stream); break;
+        case T_Q5_1: rc = dispatch_dtype<T_Q5_1>(W, X, Y, xy_dtype, B, K, N, ws, stream); break;
+        case T_Q8_0: rc = dispatch_dtype<T_Q8_0>(W, X, Y, xy_dtype, B, K, N, ws, stream); break;
         default: return 1;
     }
     if (rc != 1 || B < 6 || ggb_current_yout() || ggb_current_xin()) return rc;

@@ -56,6 +56,7 @@ struct RgParams {
     int x_vec;
     int pdl_prefetch;
     int dbg;
+    int share;           // the CTAs of a cluster share the activation quantization (else a cluster launch only places the CTAs)
     unsigned long long *trace;
 };
 
@@ -181,8 +182,14 @@ __device__ __forceinline__ long long clk64() {
 // S = row chunks in flight per warp (ring stages): 4 where the ring fits beside the activations in half an SM's shared
 // memory (K = 4096: 12 warps x 4 x 2304 B + 5 KB = exactly the 113 KB two resident CTAs may have each), else 3.
 // FULL = every chunk has 16 super-blocks (K % 4096 == 0): all lanes own an item and the copy needs no bounds.
+// Registers.  The register file is split over the four SM sub-partitions (16 K registers each) and the warps of a CTA are dealt
+// round-robin: a 12-warp CTA (3 warps per sub-partition x 80 registers = 7680) leaves room for 8704, a 14-warp CTA puts 4 warps on
+// two of them -- at 72 registers (9216) the two kinds could NOT share an SM, although two 12-warp or two 14-warp CTAs can: in the
+// 70B block (gate|up: 12 warps, down: 14) every SM then held two CTAs of one launch or none, the gate|up launch ran on 74 SMs and
+// took 49 us instead of 41 (%smid stamps, profiles/r02_block_trace.log).  The 14-warp variant is therefore compiled for 64
+// registers (bounds of 512 threads x 2; 24 bytes of spill stores outside the dot products).
 template <int TYPE, typename T, int S, bool FULL, int NW>
-__global__ void __launch_bounds__(NW * 32, 2)
+__global__ void __launch_bounds__(NW == 14 ? 512 : NW * 32, 2)
 mmvq_rg_kernel(const RgParams p) {
     using Ops = RgOps<TYPE>;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -209,7 +216,7 @@ mmvq_rg_kernel(const RgParams p) {
     // Cluster of CL CTAs (launch attribute; CL = 1: none): each CTA quantizes 1 / CL of the activation row and writes its part
     // into every CTA's shared memory (DSMEM), so the row is read from L2 and quantized CL times less often per SM.  The
     // arrive here / wait before the first remote store proves that every CTA of the cluster has started.
-    const uint32_t CL = p.image == nullptr ? cluster_nctarank() : 1u, crank = CL > 1 ? cluster_ctarank() : 0u;
+    const uint32_t CL = p.share ? cluster_nctarank() : 1u, crank = CL > 1 ? cluster_ctarank() : 0u;
     uint64_t *act_bar = reinterpret_cast<uint64_t *>(smem + p.off_bar);        // counts the bytes of the image as they land (CL > 1)
     if (CL > 1) {
         if (tid == 0) {
@@ -485,6 +492,7 @@ int launch_cfg(RgParams &p, int grid, int smem, int cluster, cudaStream_t stream
                                                    : pol == 2 ? cudaClusterSchedulingPolicyLoadBalancing : cudaClusterSchedulingPolicySpread;
     cfg.attrs = attr;
     cfg.numAttrs = cluster > 1 ? 3 : 1;
+    GGB_CUDA_TRY((ggb_prefer_max_smem_once<mmvq_rg_kernel<TYPE, T, S, FULL, NW>>(di.dev)));
     GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmvq_rg_kernel<TYPE, T, S, FULL, NW>, p));
     return GGB_OK;
 }
@@ -522,6 +530,13 @@ int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, const vo
     int cluster = (ggb_sb::g_rg_mode >> 20) & 0xf;
     if (cluster != 1 && cluster != 2 && cluster != 4) cluster = K >= 8192 ? kDefaultCluster : 1;   // short rows: the pass is a latency chain, splitting it gains nothing
     if (image != nullptr || grid < 2 * cluster) cluster = 1;
+    p.share = cluster > 1;
+    // Placement.  Two CTAs fit on an SM (this launch and the next are meant to share it), and a plain launch onto idle SMs was
+    // seen to put TWO of its CTAs on every second SM (per-CTA %smid stamps, profiles/r02_block_trace.log: 72 SMs with two CTAs
+    // of a launch, 72 with none -- and the launch after it inherits the other slots, so the pattern persists).  A cluster launch
+    // with the spread policy puts the CTAs of a pair on different SMs; it is used for placement even when nothing is shared.
+    const int place = (ggb_sb::g_rg_mode >> 26) & 1 ? 1 : 2;               // debug bit 26: plain launches
+    if (cluster == 1 && place == 2 && grid >= 4) cluster = 2;
     grid = (grid + cluster - 1) / cluster * cluster;       // (CTAs past the last row quantize their share and exit)
     if (grid > di.sm_count) grid -= cluster;
     p.part_rows = p.C > 1 ? (int)((N + grid - 1) / grid + 1) : 0;
@@ -530,7 +545,7 @@ int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, const vo
     // a pre-launched image is read straight into registers: no activation area in shared memory, the ring gets the room
     p.off_part = image != nullptr ? 0 : p.off_scales + 2 * p.ipr * 16;
     p.off_bar = (p.off_part + p.part_rows * p.C * 4 + 7) & ~7;                // (only a cluster launch uses it)
-    p.off_slots = (p.off_bar + (cluster > 1 ? 8 : 0) + 127) & ~127;
+    p.off_slots = (p.off_bar + (p.share ? 8 : 0) + 127) & ~127;
     const int half_sm = (di.max_smem_optin + 1024) / 2 - 1024;               // two CTAs per SM
     const int force_s = (ggb_sb::g_rg_mode >> 12) & 0xf;                     // debug: 3 or 4 stages
     constexpr int stage_bytes = 16 * Ops::BS;

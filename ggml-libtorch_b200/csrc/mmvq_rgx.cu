@@ -245,6 +245,7 @@ int launch_s(RgxParams &p, int grid, int smem, cudaStream_t stream) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    GGB_CUDA_TRY((ggb_prefer_max_smem_once<mmvq_rgx_kernel<TYPE, T, S>>(di.dev)));
     GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmvq_rgx_kernel<TYPE, T, S>, p));
     return GGB_OK;
 }

@@ -861,6 +861,7 @@ int launch_prequant(const void *X, int64_t K, void *image, cudaStream_t stream) 
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    GGB_CUDA_TRY((ggb_prefer_max_smem_once<mmvq_sb_prequant_kernel<TYPE, B, T>>(ggb_device_info().dev)));
     GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmvq_sb_prequant_kernel<TYPE, B, T>, X, xin, (int)K, x_vec, static_cast<uint8_t *>(image),
                                     (int)((B * K + 15) & ~(int64_t)15)));
     return GGB_OK;
@@ -937,6 +938,7 @@ int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, const vo
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    GGB_CUDA_TRY((ggb_prefer_max_smem_once<mmvq_sb_kernel<TYPE, B, T, NW>>(di.dev)));
     GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmvq_sb_kernel<TYPE, B, T, NW>, p, g_defer_reduce));
     return GGB_OK;
 }

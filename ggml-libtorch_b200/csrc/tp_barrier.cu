@@ -84,6 +84,7 @@ extern "C" int ggb_tp_barrier(void *const *flag_peers, int n_peers, int rank, vo
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    GGB_CUDA_TRY((ggb_prefer_max_smem_once<tp_barrier_kernel>(ggb_device_info().dev)));
     GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tp_barrier_kernel, peers, n_peers, rank));
     return GGB_OK;
 }

@@ -36,6 +36,9 @@ if rg and B == 1 and t == 12:
     # rg kernel: 8 stamps per CTA: clock64 at start, dep-wait done, first X loads landed, quantized, activations in registers,
     # first 4 rows done, end; [7] = globaltimer at start
     tr = raw.reshape(nl, 256, 8)[:, :148]
+    for i in range(nl):
+        cnt = np.bincount(tr[i, :, 7] & 0xff, minlength=148)[:148]
+        print(f"launch {i}: {int((cnt == 0).sum())} SMs without a CTA, {int((cnt == 1).sum())} with one, {int((cnt >= 2).sum())} with two")
     tr[:, :, 7] &= ~0xff
     tr = tr.astype(np.float64)
     g0 = tr[0, :, 7].min()
