@@ -1,4 +1,5 @@
-// mmvq_rg.cu -- batch-1 MMVQ with the q8_1 activations RESIDENT IN REGISTERS (Q4_K; K % 256 == 0, K <= 16384, 24576, 28672).
+// mmvq_rg.cu -- batch-1 MMVQ with the q8_1 activations RESIDENT IN REGISTERS (Q4_K: K % 256 == 0, K <= 16384, 24576, 28672;
+// Q6_K: K % 2048 == 0, the same row lengths).
 //
 // Same contract as the other MMVQ kernels (ggml_mul_mat_vec_a8 = quantize_row_q8_1_cuda + mul_mat_vec_q + vec_dot_q4_K_q8_1,
 // hf-kernels/ggml-kernels/ggml/ggml_kernel.cu:13-66,80-193; ggml/mmvq.cuh:2-38; ggml/vecdotq.cuh:266-327).
@@ -111,6 +112,8 @@ template <int TYPE> struct RgOps;
 // ---- Q4_K: one 128-value item (half h of a 144-byte super-block) against the lane's resident activations
 template <> struct RgOps<T_Q4_K> {
     static constexpr int BS = 144;
+    // second activation word per 32-value group: d8 * sum(q8) (the minima's factor)
+    __device__ __forceinline__ static uint32_t aux_word(float d8, int s_lo16, int s_hi16) { return __float_as_uint(d8 * (float)(s_lo16 + s_hi16)); }
     // hdp: the lane's super-block header in the ring stage (the chunk's bytes as they lie in memory); qsp: the 64 bytes of
     // nibbles of its half h (32-bit shared-memory addresses)
     __device__ __forceinline__ static float item(uint32_t hdp, uint32_t qsp, const uint32_t (&a)[32], const float4 d8,
@@ -151,6 +154,80 @@ template <> struct RgOps<T_Q4_K> {
     }
 };
 
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t addr) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return v;
+}
+// N consecutive 32-bit words from a 2-byte-aligned shared address: N + 1 aligned loads + funnel shifts (sh = 0 or 16)
+template <int N>
+__device__ __forceinline__ void lds_words(uint32_t addr_al, uint32_t sh, uint32_t (&out)[N]) {
+    uint32_t w[N + 1];
+#pragma unroll
+    for (int i = 0; i <= N; i++) w[i] = lds32(addr_al + 4 * i);
+#pragma unroll
+    for (int i = 0; i < N; i++) out[i] = __funnelshift_r(w[i], w[i + 1], sh);
+}
+
+// ---- Q6_K: ql[128] @0, qh[64] @128, 16 int8 scales @192 (one per 16 values), d @208; 210-byte super-blocks are 2-byte aligned
+// (in the stage: 4-byte aligned for even super-blocks, 2 bytes off for odd ones).  Value = d * sc * (q6 - 32)
+// (dequantize.cuh:230-254, vecdotq.cuh:331-349).  The item = half h: values 128 h .. 128 h + 127 = four groups j of 32:
+//   j = 0: ql[64h + l] & 15 | (qh[32h + l] & 3) << 4        j = 1: ql[64h + 32 + l] & 15 | (qh >> 2 & 3) << 4
+//   j = 2: ql[64h + l] >> 4 | (qh >> 4 & 3) << 4            j = 3: ql[64h + 32 + l] >> 4 | (qh >> 6 & 3) << 4      (l = 0..31)
+// with scale byte 8h + 2j + l / 16.  The weights go to dp4a as the unsigned q6; the -32 comes back through the sums of the q8
+// quants over each 16-value half (second activation word: two int16), all in integers: t = sum_u sc_u * (dot_u - 32 * sq_u).
+template <> struct RgOps<T_Q6_K> {
+    static constexpr int BS = 210;
+    __device__ __forceinline__ static uint32_t aux_word(float, int s_lo16, int s_hi16) { return ((uint32_t)s_lo16 & 0xffffu) | ((uint32_t)s_hi16 << 16); }
+    __device__ __forceinline__ static float item(uint32_t hp, const uint32_t (&a)[32], const float4 d8, const float4 ds, int h) {
+        const uint32_t sh = (hp & 2u) * 8u, al = hp & ~3u;
+        uint32_t qh[8], scw[2];
+        lds_words<8>(al + 128 + 32 * h, sh, qh);
+        lds_words<2>(al + 192 + 8 * h, sh, scw);
+        const float d = ggb_h2f((uint16_t)lds16(hp + 208));
+        int dot[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+        {
+            uint32_t ql[8];
+            lds_words<8>(al + 64 * h, sh, ql);
+#pragma unroll
+            for (int w = 0; w < 8; w++) {
+                const uint32_t q0 = (ql[w] & 0x0f0f0f0fu) | ((qh[w] << 4) & 0x30303030u);
+                const uint32_t q2 = ((ql[w] >> 4) & 0x0f0f0f0fu) | (qh[w] & 0x30303030u);
+                dot[0][w >> 2] = dp4a_us(q0, a[w], dot[0][w >> 2]);
+                dot[2][w >> 2] = dp4a_us(q2, a[16 + w], dot[2][w >> 2]);
+            }
+        }
+        {
+            uint32_t ql[8];
+            lds_words<8>(al + 64 * h + 32, sh, ql);
+#pragma unroll
+            for (int w = 0; w < 8; w++) {
+                const uint32_t q1 = (ql[w] & 0x0f0f0f0fu) | ((qh[w] << 2) & 0x30303030u);
+                const uint32_t q3 = ((ql[w] >> 4) & 0x0f0f0f0fu) | ((qh[w] >> 2) & 0x30303030u);
+                dot[1][w >> 2] = dp4a_us(q1, a[8 + w], dot[1][w >> 2]);
+                dot[3][w >> 2] = dp4a_us(q3, a[24 + w], dot[3][w >> 2]);
+            }
+        }
+        const float d8v[4] = {d8.x, d8.y, d8.z, d8.w};
+        const uint32_t sqv[4] = {__float_as_uint(ds.x), __float_as_uint(ds.y), __float_as_uint(ds.z), __float_as_uint(ds.w)};
+        float f = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t sw = scw[j >> 1] >> (16 * (j & 1));
+            const int s0 = (int)(int8_t)(sw & 0xffu), s1 = (int)(int8_t)((sw >> 8) & 0xffu);
+            const int sq0 = (int)(int16_t)(sqv[j] & 0xffffu), sq1 = (int)(int16_t)(sqv[j] >> 16);
+            const int t = (dot[j][0] - 32 * sq0) * s0 + (dot[j][1] - 32 * sq1) * s1;
+            f = fmaf(d8v[j], (float)t, f);
+        }
+        return d * f;
+    }
+};
+
 // 16-byte asynchronous copy global -> shared (LDGSTS), L2 only, evict-first
 __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void *gsrc, uint64_t policy) {
     asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "l"(policy) : "memory");
@@ -182,6 +259,43 @@ __device__ __forceinline__ long long clk64() {
 // S = row chunks in flight per warp (ring stages): 4 where the ring fits beside the activations in half an SM's shared
 // memory (K = 4096: 12 warps x 4 x 2304 B + 5 KB = exactly the 113 KB two resident CTAs may have each), else 3.
 // FULL = every chunk has 16 super-blocks (K % 4096 == 0): all lanes own an item and the copy needs no bounds.
+// The activation image as its own small launch, in THIS kernel's layout ([8][ipr] quants | [2][ipr] {d8 x 4 | aux x 4}): used where
+// the in-kernel pass is too slow for the warps the GEMV has (Q6_K, K = 28672 with the fused SwiGLU: 7 x 2 warps, 28672 exponentials).
+// 128 threads = one warp per register bank at <= 40 registers: a CTA of it fits beside the GEMV's CTA and its neighbour's on every
+// SM (see "Registers" below), so it does not keep the GEMV's CTAs from becoming resident early.
+template <int TYPE, typename T>
+__global__ void __launch_bounds__(128)
+mmvq_rg_prequant_kernel(const T *__restrict__ X, const GgbXIn xin, const int K, const int x_vec, uint8_t *__restrict__ image, const int off_scales) {
+    using Ops = RgOps<TYPE>;
+    ggb_pdl_launch_dependents();
+    ggb_pdl_wait();
+    const int ipr = K >> 7, ngroups = K >> 5;
+    const int t4 = threadIdx.x & 3;
+    const int g = blockIdx.x * 32 + (threadIdx.x >> 2);
+    float v[8];
+    if (g < ngroups) {
+        load_act8<T>(X, static_cast<const T *>(xin.x2), xin.ldx, 0, g * 32 + t4 * 8, x_vec != 0, v);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = 0.0f;
+    }
+    const Q8Group q = q8_1_quantize_group<false>(v);
+    int mine = __dp4a((int)q.q_lo, 0x01010101, __dp4a((int)q.q_hi, 0x01010101, 0));
+    mine += __shfl_xor_sync(0xffffffffu, mine, 1);
+    const int other = __shfl_xor_sync(0xffffffffu, mine, 2);
+    if (g < ngroups) {
+        const int it = g >> 2, j = g & 3, i = 2 * j + (t4 >> 1);
+        const float d8 = __half2float(__float2half_rn(q.d));
+        uint4 *act_q = reinterpret_cast<uint4 *>(image);
+        uint4 *act_s = reinterpret_cast<uint4 *>(image + off_scales);
+        *reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(act_q + i * ipr + it) + 8 * (t4 & 1)) = make_uint2(q.q_lo, q.q_hi);
+        if (t4 == 0) {
+            reinterpret_cast<float *>(act_s + it)[j] = d8;
+            reinterpret_cast<uint32_t *>(act_s + ipr + it)[j] = Ops::aux_word(d8, mine, other);
+        }
+    }
+}
+
 // Registers.  The register file is split over the four SM sub-partitions (16 K registers each) and the warps of a CTA are dealt
 // round-robin: a 12-warp CTA (3 warps per sub-partition x 80 registers = 7680) leaves room for 8704, a 14-warp CTA puts 4 warps on
 // two of them -- at 72 registers (9216) the two kinds could NOT share an SM, although two 12-warp or two 14-warp CTAs can: in the
@@ -233,7 +347,7 @@ mmvq_rg_kernel(const RgParams p) {
     const int my_rows = (rl < RW && nrows > rl) ? (nrows - rl + RW - 1) / RW : 0;
     const int sb0 = c * p.spc;                                   // first super-block of the chunk
     const int nsb_c = FULL ? 16 : min(p.spc, p.nsb - sb0);       // super-blocks in it
-    const int n16 = nsb_c * (Ops::BS / 16);                      // 16-byte pieces per row chunk
+    const int n16 = nsb_c * Ops::BS / 16;                        // 16-byte pieces per row chunk (the launcher keeps chunks whole)
     const int sbl = lane >> 1, h = lane & 1;                     // this lane's item: half h of super-block sb0 + sbl
     const bool live = FULL || sbl < nsb_c;
     const int item = 2 * (sb0 + sbl) + h;
@@ -249,24 +363,22 @@ mmvq_rg_kernel(const RgParams p) {
 
     // this lane's pieces of a row chunk: lane, lane + 32, ... (npc of them).  The source advances by one row per request.
     const int npc = (n16 - lane + 31) >> 5;
-    const int lo16 = lane < 16;
     const uint8_t *src_next = p.W + (r_begin + rl) * (int64_t)p.row_bytes + (int64_t)sb0 * Ops::BS + lane * 16;
     int to_issue = my_rows;
+    constexpr int NP16 = stage_bytes / 16;                       // 16-byte pieces of a full row chunk (Q4_K: 144, Q6_K: 210)
+    constexpr int NPQ = (NP16 + 31) / 32;                        // ... per lane, rounded up
+    constexpr int LAST_LANES = NP16 - 32 * (NPQ - 1);            // lanes that own a piece in the last round (16 / 18)
+    const int lo_last = lane < LAST_LANES;
     auto issue_row = [&](uint32_t dst) {          // this warp's next row -> the stage at dst (an empty group past the end)
         const int go = to_issue > 0;
         if (FULL) {
-            cp_async16_if(go, 0, dst, src_next, pol);
-            cp_async16_if(go, 0, dst + 512, src_next + 512, pol);
-            cp_async16_if(go, 0, dst + 1024, src_next + 1024, pol);
-            cp_async16_if(go, 0, dst + 1536, src_next + 1536, pol);
-            cp_async16_if(go & lo16, 0, dst + 2048, src_next + 2048, pol);
+#pragma unroll
+            for (int q = 0; q < NPQ - 1; q++) cp_async16_if(go, 0, dst + 512 * q, src_next + 512 * q, pol);
+            cp_async16_if(go & lo_last, 0, dst + 512 * (NPQ - 1), src_next + 512 * (NPQ - 1), pol);
         } else {
             const int have = go ? npc : 0;
-            cp_async16_if(have, 0, dst, src_next, pol);
-            cp_async16_if(have, 1, dst + 512, src_next + 512, pol);
-            cp_async16_if(have, 2, dst + 1024, src_next + 1024, pol);
-            cp_async16_if(have, 3, dst + 1536, src_next + 1536, pol);
-            cp_async16_if(have, 4, dst + 2048, src_next + 2048, pol);
+#pragma unroll
+            for (int q = 0; q < NPQ; q++) cp_async16_if(have, q, dst + 512 * q, src_next + 512 * q, pol);
         }
         cp_async_commit();
         src_next += p.wstep;
@@ -331,7 +443,7 @@ mmvq_rg_kernel(const RgParams p) {
                     *reinterpret_cast<uint2 *>(dst) = make_uint2(q.q_lo, q.q_hi);
                     if (t4 == 0) {
                         reinterpret_cast<float *>(act_s + it)[j] = d8;
-                        reinterpret_cast<float *>(act_s + ipr + it)[j] = d8 * (float)(mine + other);
+                        reinterpret_cast<uint32_t *>(act_s + ipr + it)[j] = Ops::aux_word(d8, mine, other);
                     }
                 } else {
                     const uint32_t qa = act_q_s + (uint32_t)(i * ipr + it) * 16u + 8u * (t4 & 1);
@@ -342,7 +454,7 @@ mmvq_rg_kernel(const RgParams p) {
                         st_async_v2(mapa(qa, r), q.q_lo, q.q_hi, mb);
                         if (t4 == 0) {
                             st_async_f32(mapa(sa, r), d8, mb);
-                            st_async_f32(mapa(sa + (uint32_t)ipr * 16u, r), d8 * (float)(mine + other), mb);
+                            st_async_f32(mapa(sa + (uint32_t)ipr * 16u, r), __uint_as_float(Ops::aux_word(d8, mine, other)), mb);
                         }
                     }
                 }
@@ -424,7 +536,9 @@ mmvq_rg_kernel(const RgParams p) {
                 const uint32_t dp = (S == 4) ? ring_k + jj * stage_bytes : dstp;
                 cp_async_wait<S - 1>();                                // this thread's pieces of the oldest row have landed
                 __syncwarp();                                          // ... and so have the other lanes'
-                const float v = Ops::item(hp, hp + qoff, a, d8, ds, h);
+                float v;
+                if constexpr (TYPE == T_Q4_K) v = Ops::item(hp, hp + qoff, a, d8, ds, h);
+                else v = Ops::item(hp, a, d8, ds, h);
                 part[jj] = (FULL || live) ? v : 0.0f;
                 __syncwarp();                                          // every lane has read the stage
                 issue_row(dp);                                         // refill it
@@ -513,10 +627,21 @@ int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, const vo
     p.ipr = 2 * p.nsb;
     p.row_bytes = p.nsb * Ops::BS;
     p.C = (p.nsb + 15) / 16;
-    const int nw = (p.C == 7) ? 14 : 12;
+    constexpr bool Q6 = TYPE == T_Q6_K;
+    // warps: 12; seven chunks (K = 28672) take 14 (Q4_K) or 7 (Q6_K: its 3360-byte stages leave room for one row lane only)
+    const int nw = (p.C == 7) ? (Q6 ? 7 : 14) : 12;
     const bool full = p.nsb % 16 == 0;
-    if (p.C > 7 || nw % p.C != 0 || p.row_bytes % 16 != 0 || (nw == 14 && !full)) return 1;
+    if (p.C > 7 || nw % p.C != 0 || p.row_bytes % 16 != 0 || (p.C == 7 && !full)) return 1;
+    // Q6_K, K = 28672 with the fused SwiGLU activation: 7 warps x 2 CTAs would spend 4.6 us on the 28672 exponentials (70B block
+    // 91.3 us): that case takes its activations from the pre-launch above (ggb_mmvq_rg_wants_image / ggb_mmvq_rg_prequant)
+    if (Q6 && p.C == 7 && p.xin.x2 != nullptr && image == nullptr) return 1;
+    // balanced chunks when every chunk then starts and ends on a 16-byte boundary (Q6_K: multiples of 8 super-blocks), else
+    // 16-super-block chunks and a shorter last one
     p.spc = (p.nsb + p.C - 1) / p.C;
+    if ((p.spc * Ops::BS) % 16 != 0 || ((p.nsb - (p.C - 1) * p.spc) * Ops::BS) % 16 != 0) {
+        p.spc = 16;
+        if (((p.nsb - (p.C - 1) * 16) * Ops::BS) % 16 != 0) return 1;
+    }
     p.RW = nw / p.C;
     p.wstep = (long long)p.RW * p.row_bytes;
     p.x_vec = (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.xin.x2) & 15) == 0 &&
@@ -552,17 +677,25 @@ int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, const vo
     int S = 4;
     while (S > 2 && p.off_slots + nw * S * stage_bytes > half_sm) S--;
     if (force_s == 3 && S > 3) S = 3;
-    if (nw == 14 && S > 3) S = 3;                                             // (instantiated: 12 warps x {3, 4}, 14 warps x {2, 3})
-    if (nw == 12 && S < 3) return 1;
+    // instantiated -- Q4_K: 12 warps x {3, 4} stages, 14 warps x {2, 3}; Q6_K: 12 warps x 2, 7 warps x {2, 3}
+    if (nw != 12 && S > 3) S = 3;
+    if (Q6 && nw == 12) S = 2;
+    if (!Q6 && nw == 12 && S < 3) return 1;
     const int smem = p.off_slots + nw * S * stage_bytes;
     if (smem > half_sm) return 1;
     if (probe_only) return 2;
     if (p.early == 0 || p.early > S) p.early = 1;
     p.trace = ggb_mmvq_trace_slot();
-    if (nw == 14)
-        return S == 3 ? launch_cfg<TYPE, T, 3, true, 14>(p, grid, smem, cluster, stream) : launch_cfg<TYPE, T, 2, true, 14>(p, grid, smem, cluster, stream);
-    if (S == 4) return full ? launch_cfg<TYPE, T, 4, true, 12>(p, grid, smem, cluster, stream) : launch_cfg<TYPE, T, 4, false, 12>(p, grid, smem, cluster, stream);
-    return full ? launch_cfg<TYPE, T, 3, true, 12>(p, grid, smem, cluster, stream) : launch_cfg<TYPE, T, 3, false, 12>(p, grid, smem, cluster, stream);
+    if constexpr (Q6) {
+        if (nw == 7)
+            return S == 3 ? launch_cfg<TYPE, T, 3, true, 7>(p, grid, smem, cluster, stream) : launch_cfg<TYPE, T, 2, true, 7>(p, grid, smem, cluster, stream);
+        return full ? launch_cfg<TYPE, T, 2, true, 12>(p, grid, smem, cluster, stream) : launch_cfg<TYPE, T, 2, false, 12>(p, grid, smem, cluster, stream);
+    } else {
+        if (nw == 14)
+            return S == 3 ? launch_cfg<TYPE, T, 3, true, 14>(p, grid, smem, cluster, stream) : launch_cfg<TYPE, T, 2, true, 14>(p, grid, smem, cluster, stream);
+        if (S == 4) return full ? launch_cfg<TYPE, T, 4, true, 12>(p, grid, smem, cluster, stream) : launch_cfg<TYPE, T, 4, false, 12>(p, grid, smem, cluster, stream);
+        return full ? launch_cfg<TYPE, T, 3, true, 12>(p, grid, smem, cluster, stream) : launch_cfg<TYPE, T, 3, false, 12>(p, grid, smem, cluster, stream);
+    }
 }
 
 template <int TYPE>
@@ -587,6 +720,46 @@ int ggb_mmvq_rg_impl(const void *W, const void *X, void *Y, int type, int xy_dty
     if (!(ggb_sb::g_rg_mode & 1) || B != 1 || K % 256 != 0 || K > 28672 || (reinterpret_cast<uintptr_t>(W) & 15)) return 1;
     switch (type) {
         case T_Q4_K: return dispatch_dtype<T_Q4_K>(W, X, Y, xy_dtype, K, N, image, probe_only, stream);
+        case T_Q6_K: return (K % 2048 == 0 && (ggb_sb::g_rg_mode & (1 << 27)) == 0)        // (debug bit 27: Q6_K stays on the ring kernel)
+                                ? dispatch_dtype<T_Q6_K>(W, X, Y, xy_dtype, K, N, image, probe_only, stream) : 1;
+        default: return 1;
+    }
+}
+
+// The one case that wants its activation image pre-launched in this kernel's layout (see mmvq_rg_prequant_kernel)
+int ggb_mmvq_rg_wants_image(int type, int64_t B, int64_t K, const void *x2) {
+    return (ggb_sb::g_rg_mode & 1) && !(ggb_sb::g_rg_mode & (1 << 27)) && type == T_Q6_K && B == 1 && x2 != nullptr && K == 28672;
+}
+int64_t ggb_mmvq_rg_image_bytes(int64_t K) { return ((K + 15) & ~(int64_t)15) + 2 * (K / 128) * 16; }
+
+namespace {
+template <int TYPE, typename T>
+int launch_prequant(const void *X, int64_t K, void *image, cudaStream_t stream) {
+    const GgbXIn xin = ggb_make_xin(K);
+    const int x_vec = (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(xin.x2) & 15) == 0 &&
+                      (xin.ldx * (int64_t)sizeof(T)) % 16 == 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((K / 32 + 31) / 32));
+    cfg.blockDim = dim3(128);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    GGB_CUDA_TRY((ggb_prefer_max_smem_once<mmvq_rg_prequant_kernel<TYPE, T>>(ggb_device_info().dev)));
+    GGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, mmvq_rg_prequant_kernel<TYPE, T>, static_cast<const T *>(X), xin, (int)K, x_vec,
+                                    static_cast<uint8_t *>(image), (int)((K + 15) & ~(int64_t)15)));
+    return GGB_OK;
+}
+}  // namespace
+
+int ggb_mmvq_rg_prequant(const void *X, int type, int xy_dtype, int64_t K, void *image, cudaStream_t stream) {
+    if (type != T_Q6_K) return 1;
+    switch (xy_dtype) {
+        case GGB_F32:  return launch_prequant<T_Q6_K, float>(X, K, image, stream);
+        case GGB_F16:  return launch_prequant<T_Q6_K, __half>(X, K, image, stream);
+        case GGB_BF16: return launch_prequant<T_Q6_K, __nv_bfloat16>(X, K, image, stream);
         default: return 1;
     }
 }

@@ -60,6 +60,9 @@ int ggb_mmvq_rgx_impl(const void *W, const void *X, void *Y, int type, int xy_dt
                       cudaStream_t stream);
 namespace ggb_sb { extern int g_rg_mode; }
 int ggb_mmvq_sb_prequant_q4k_b1(const void *X, int xy_dtype, int64_t K, void *image, cudaStream_t stream);
+int ggb_mmvq_rg_wants_image(int type, int64_t B, int64_t K, const void *x2);
+int64_t ggb_mmvq_rg_image_bytes(int64_t K);
+int ggb_mmvq_rg_prequant(const void *X, int type, int xy_dtype, int64_t K, void *image, cudaStream_t stream);
 
 // bytes of the pre-launched activation image ggb_mmvq_sb_impl would use for (type, B, K); 0 = it quantizes in-kernel
 int64_t ggb_mmvq_sb_workspace_bytes(int type, int64_t B, int64_t K) {
@@ -78,11 +81,21 @@ void ggb_mmvq_sb_set_prequant_min_k(int k) { g_prequant_min_k = k < 0 ? 0 : k; }
 int ggb_mmvq_sb_impl(const void *W, const void *X, void *Y, int type, int xy_dtype, int64_t B, int64_t K, int64_t N,
                      void *ws, int64_t ws_bytes, cudaStream_t stream) {
     if (K % 256 != 0 || K > (1 << 20) || (reinterpret_cast<uintptr_t>(W) & 15)) return 1;
+    const GgbXIn xin = ggb_make_xin(K);
+    // Q6_K, K = 28672, fused SwiGLU: the register kernel behind its own activation pre-launch (mmvq_rg.cu)
+    if (ggb_mmvq_rg_wants_image(type, B, K, xin.x2) && ws != nullptr && (reinterpret_cast<uintptr_t>(ws) & 15) == 0 &&
+        ws_bytes >= ggb_mmvq_rg_image_bytes(K) && ggb_mmvq_rg_impl(W, X, Y, type, xy_dtype, B, K, N, ws, 1, stream) == 2) {
+        const int rc = ggb_mmvq_rg_prequant(X, type, xy_dtype, K, ws, stream);
+        if (rc != GGB_OK) return rc;
+        return ggb_mmvq_rg_impl(W, X, Y, type, xy_dtype, B, K, N, ws, 0, stream);
+    }
     if (ggb_mmvq_rg_impl(W, X, Y, type, xy_dtype, B, K, N, nullptr, 1, stream) == 2) {
         const void *image = nullptr;
-        const GgbXIn xin = ggb_make_xin(K);
-        if (ws != nullptr && (reinterpret_cast<uintptr_t>(ws) & 15) == 0 && ws_bytes >= ggb_mmvq_sb_run_q4k_image_bytes(1, K) &&
-            g_prequant_min_k > 0 && (K >= g_prequant_min_k || (xin.x2 != nullptr && K >= 4096))) {
+        // (the register kernel shares its activation quantization -- SwiGLU included -- across a CTA pair; a pre-launch in front of
+        // it measured slower in the 70B block, 81.0 vs 73.2 us: its CTAs keep 14 SMs from taking their CTA of the GEMV early.  Only
+        // an explicit row-length threshold asks for it.)
+        if (type == T_Q4_K && ws != nullptr && (reinterpret_cast<uintptr_t>(ws) & 15) == 0 &&
+            ws_bytes >= ggb_mmvq_sb_run_q4k_image_bytes(1, K) && g_prequant_min_k > 0 && K >= g_prequant_min_k) {
             const int rc = ggb_mmvq_sb_prequant_q4k_b1(X, xy_dtype, K, ws, stream);
             if (rc != GGB_OK) return rc;
             image = ws;

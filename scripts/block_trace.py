@@ -10,20 +10,21 @@ ggml.set_option(ggml.GGB_OPT_STATIC_WEIGHTS, 1)
 for a in sys.argv[1:]:
     if a.startswith("opt:"):
         k, v = a[4:].split("="); L.ggb_set_option(int(k), int(v))
-td = int(os.environ.get("TD", "12")); plain = os.environ.get("PLAIN", "0") == "1"
-H, I, B, NB = 8192, 28672, 1, 4
+tds = [int(v) for v in os.environ.get("TD", "12").split(",")]; plain = os.environ.get("PLAIN", "0") == "1"
+H, I, B = 8192, 28672, 1
+NB = max(4, len(tds))
+tds = (tds * NB)[:NB]
 dev = torch.device("cuda")
 gu_w = [torch.from_numpy(synth.random_blocks(12, 2 * I, H, seed=1)).to(dev) for _ in range(1)]
 gu_w += [gu_w[0].clone() for _ in range(NB - 1)]
-dn_w = [torch.from_numpy(synth.random_blocks(td, H, I, seed=2)).to(dev)]
-dn_w += [dn_w[0].clone() for _ in range(NB - 1)]
+dn_w = [torch.from_numpy(synth.random_blocks(t, H, I, seed=2)).to(dev) for t in tds]
 x = torch.randn(B, H, dtype=torch.float16, device=dev)
 gu = torch.randn(8, 2 * I, dtype=torch.float16, device=dev); dn = torch.empty(8, H, dtype=torch.float16, device=dev)
 h = torch.randn(B, I, dtype=torch.float16, device=dev)
-need = max(ggml.mmvq_workspace_bytes(12, B, H, 2 * I), ggml.mmvq_workspace_bytes(td, B, I, H), 16)
+need = max([ggml.mmvq_workspace_bytes(12, B, H, 2 * I), 16] + [ggml.mmvq_workspace_bytes(t, B, I, H) for t in tds])
 ws = torch.empty(need, dtype=torch.uint8, device=dev)
 def blocks():
-    for wg, wd in zip(gu_w, dn_w):
+    for wg, wd, td in zip(gu_w, dn_w, tds):
         ggml.mul_mat_vec_a8_fused(wg, x, None, 12, 2 * I, [gu.data_ptr()], 2 * I, 0, I, I, ws)
         if plain: ggml.mul_mat_vec_a8_fused(wd, h, None, td, H, [dn.data_ptr()], H, 0, 0, 0, ws)
         else: ggml.mul_mat_vec_a8_fused(wd, gu[:B, :I], gu[:B, I:], td, H, [dn.data_ptr()], H, 0, 0, 0, ws)
@@ -46,7 +47,7 @@ raw[:, :, 7] &= ~0xff
 tr = raw.astype(np.float64)
 for i in range(nl):
     cnt = np.bincount(smid[i], minlength=148)[:148]
-    print(f"launch {i}: CTAs per SM: {int((cnt == 0).sum())} SMs with none, {int((cnt == 1).sum())} with one, {int((cnt >= 2).sum())} with two or more")
+    print(f"launch {i} ({'gu' if i % 2 == 0 else 'down type %d' % tds[i // 2]}): CTAs per SM: {int((cnt == 0).sum())} SMs with none, {int((cnt == 1).sum())} with one, {int((cnt >= 2).sum())} with two or more")
 clk = 1.965e3   # cycles per us
 g0 = tr[0, :, 7].min()
 names = ["dep", "Xin", "quant", "regs", "4rows", "end"]
