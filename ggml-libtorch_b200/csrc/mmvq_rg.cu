@@ -629,7 +629,9 @@ int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, const vo
     p.C = (p.nsb + 15) / 16;
     constexpr bool Q6 = TYPE == T_Q6_K;
     // warps: 12; seven chunks (K = 28672) take 14 (Q4_K) or 7 (Q6_K: its 3360-byte stages leave room for one row lane only)
-    const int nw = (p.C == 7) ? (Q6 ? 7 : 14) : 12;
+    // (Q4_K with a pre-launched image also takes 7 warps: beside a 14-warp CTA and the 12-warp neighbour no register bank has room
+    // for a CTA of the pre-launch, beside a 7-warp one it has -- see "Registers")
+    const int nw = (p.C == 7) ? ((Q6 || image != nullptr) ? 7 : 14) : 12;
     const bool full = p.nsb % 16 == 0;
     if (p.C > 7 || nw % p.C != 0 || p.row_bytes % 16 != 0 || (p.C == 7 && !full)) return 1;
     // Q6_K, K = 28672 with the fused SwiGLU activation: 7 warps x 2 CTAs would spend 4.6 us on the 28672 exponentials (70B block
@@ -677,8 +679,9 @@ int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, const vo
     int S = 4;
     while (S > 2 && p.off_slots + nw * S * stage_bytes > half_sm) S--;
     if (force_s == 3 && S > 3) S = 3;
-    // instantiated -- Q4_K: 12 warps x {3, 4} stages, 14 warps x {2, 3}; Q6_K: 12 warps x 2, 7 warps x {2, 3}
-    if (nw != 12 && S > 3) S = 3;
+    // instantiated -- Q4_K: 12 warps x {3, 4} stages, 14 warps x {2, 3}, 7 warps x {3, 4}; Q6_K: 12 warps x 2, 7 warps x {2, 3}
+    if ((nw == 14 || (nw == 7 && Q6)) && S > 3) S = 3;
+    if (nw == 7 && !Q6 && S < 3) return 1;
     if (Q6 && nw == 12) S = 2;
     if (!Q6 && nw == 12 && S < 3) return 1;
     const int smem = p.off_slots + nw * S * stage_bytes;
@@ -693,6 +696,8 @@ int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, const vo
     } else {
         if (nw == 14)
             return S == 3 ? launch_cfg<TYPE, T, 3, true, 14>(p, grid, smem, cluster, stream) : launch_cfg<TYPE, T, 2, true, 14>(p, grid, smem, cluster, stream);
+        if (nw == 7)
+            return S == 4 ? launch_cfg<TYPE, T, 4, true, 7>(p, grid, smem, cluster, stream) : launch_cfg<TYPE, T, 3, true, 7>(p, grid, smem, cluster, stream);
         if (S == 4) return full ? launch_cfg<TYPE, T, 4, true, 12>(p, grid, smem, cluster, stream) : launch_cfg<TYPE, T, 4, false, 12>(p, grid, smem, cluster, stream);
         return full ? launch_cfg<TYPE, T, 3, true, 12>(p, grid, smem, cluster, stream) : launch_cfg<TYPE, T, 3, false, 12>(p, grid, smem, cluster, stream);
     }
@@ -728,7 +733,11 @@ int ggb_mmvq_rg_impl(const void *W, const void *X, void *Y, int type, int xy_dty
 
 // The one case that wants its activation image pre-launched in this kernel's layout (see mmvq_rg_prequant_kernel)
 int ggb_mmvq_rg_wants_image(int type, int64_t B, int64_t K, const void *x2) {
-    return (ggb_sb::g_rg_mode & 1) && !(ggb_sb::g_rg_mode & (1 << 27)) && type == T_Q6_K && B == 1 && x2 != nullptr && K == 28672;
+    // (plain rows too: measured on the 70B down projection, 7 warps behind the pre-launch vs the in-kernel pair quantization:
+    //  Q4_K 24.0 vs 26.0 us (14 warps), Q6_K 34.5 vs 37.6 us (7 warps))
+    (void)x2;
+    if (!(ggb_sb::g_rg_mode & 1) || B != 1 || K != 28672) return 0;
+    return type == T_Q4_K ? ((ggb_sb::g_rg_mode >> 28) & 1) == 0 : (type == T_Q6_K && !(ggb_sb::g_rg_mode & (1 << 27)));   // (debug bits 27 / 28: off)
 }
 int64_t ggb_mmvq_rg_image_bytes(int64_t K) { return ((K + 15) & ~(int64_t)15) + 2 * (K / 128) * 16; }
 
@@ -755,11 +764,12 @@ int launch_prequant(const void *X, int64_t K, void *image, cudaStream_t stream) 
 }  // namespace
 
 int ggb_mmvq_rg_prequant(const void *X, int type, int xy_dtype, int64_t K, void *image, cudaStream_t stream) {
-    if (type != T_Q6_K) return 1;
+    if (type != T_Q6_K && type != T_Q4_K) return 1;
+    const bool q6 = type == T_Q6_K;
     switch (xy_dtype) {
-        case GGB_F32:  return launch_prequant<T_Q6_K, float>(X, K, image, stream);
-        case GGB_F16:  return launch_prequant<T_Q6_K, __half>(X, K, image, stream);
-        case GGB_BF16: return launch_prequant<T_Q6_K, __nv_bfloat16>(X, K, image, stream);
+        case GGB_F32:  return q6 ? launch_prequant<T_Q6_K, float>(X, K, image, stream) : launch_prequant<T_Q4_K, float>(X, K, image, stream);
+        case GGB_F16:  return q6 ? launch_prequant<T_Q6_K, __half>(X, K, image, stream) : launch_prequant<T_Q4_K, __half>(X, K, image, stream);
+        case GGB_BF16: return q6 ? launch_prequant<T_Q6_K, __nv_bfloat16>(X, K, image, stream) : launch_prequant<T_Q4_K, __nv_bfloat16>(X, K, image, stream);
         default: return 1;
     }
 }
