@@ -1,5 +1,5 @@
 // mmvq_rg.cu -- batch-1 MMVQ with the q8_1 activations RESIDENT IN REGISTERS (Q4_K: K % 256 == 0, K <= 16384, 24576, 28672;
-// Q6_K: K % 2048 == 0, the same row lengths).
+// Q5_K: the same; Q6_K: K % 2048 == 0, the same row lengths).
 //
 // Same contract as the other MMVQ kernels (ggml_mul_mat_vec_a8 = quantize_row_q8_1_cuda + mul_mat_vec_q + vec_dot_q4_K_q8_1,
 // hf-kernels/ggml-kernels/ggml/ggml_kernel.cu:13-66,80-193; ggml/mmvq.cuh:2-38; ggml/vecdotq.cuh:266-327).
@@ -146,6 +146,64 @@ template <> struct RgOps<T_Q4_K> {
         fd = fmaf(d8.z, imul_to_f32(g2, byte_of<2>(sc)), fd);
         fd = fmaf(d8.w, imul_to_f32(g3 >> 4, byte_of<3>(sc)), fd);
         // minima: dmin * sum_g m_g * (d8_g * sum q8_g)    (vecdotq.cuh:280-288)
+        float t = byte_to_f32<0>(mn) * ds.x;
+        t = fmaf(byte_to_f32<1>(mn), ds.y, t);
+        t = fmaf(byte_to_f32<2>(mn), ds.z, t);
+        t = fmaf(byte_to_f32<3>(mn), ds.w, t);
+        return dm.x * fd - dm.y * t;
+    }
+};
+
+// ---- Q5_K: {d, dmin, 12 scale bytes} @0 (the Q4_K header), 32 bytes of fifth bits @16 (bit j of byte l = value l of group j),
+// 128 bytes of nibbles @48 (dequantize.cuh:204-227, vecdotq.cuh:299-327).  176-byte super-blocks are 16-byte aligned.  The item =
+// half h = groups 4h .. 4h + 3.  The fifth bits never meet the nibbles: group jj's bit plane is taken out of the (pre-shifted) qh
+// word with the mask 0x01010101 << jj and dotted separately -- dp4a gives 2^jj * sum(bit * q8), one shift per group restores 16 x.
+template <> struct RgOps<T_Q5_K> {
+    static constexpr int BS = 176;
+    __device__ __forceinline__ static uint32_t aux_word(float d8, int s_lo16, int s_hi16) { return __float_as_uint(d8 * (float)(s_lo16 + s_hi16)); }
+    __device__ __forceinline__ static float item(uint32_t hp, const uint32_t (&a)[32], const float4 d8, const float4 ds, int h) {
+        const uint4 hd = lds128(hp);
+        const uint4 h0 = lds128(hp + 16), h1 = lds128(hp + 32);
+        const float2 dm = __half22float2(*reinterpret_cast<const __half2 *>(&hd.x));
+        uint32_t sc, mn;
+        if (h) {
+            sc = (hd.w & 0x0f0f0f0fu) | ((hd.y >> 2) & 0x30303030u);
+            mn = ((hd.w >> 4) & 0x0f0f0f0fu) | ((hd.z >> 2) & 0x30303030u);
+        } else {
+            sc = hd.y & 0x3f3f3f3fu;
+            mn = hd.z & 0x3f3f3f3fu;
+        }
+        const uint32_t sh = 4u * (uint32_t)h;
+        const uint32_t qh[8] = {h0.x >> sh, h0.y >> sh, h0.z >> sh, h0.w >> sh, h1.x >> sh, h1.y >> sh, h1.z >> sh, h1.w >> sh};
+        int g0 = 0, g1 = 0, g2 = 0, g3 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+        const uint32_t qsp = hp + 48 + 64 * h;
+        {
+            const uint4 q0 = lds128(qsp), q1 = lds128(qsp + 16);
+            const uint32_t qa[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                g0 = dp4a_ss(qa[i] & 0x0f0f0f0fu, a[i], g0);
+                g1 = dp4a_us(qa[i] & 0xf0f0f0f0u, a[8 + i], g1);               // 16 x the high nibbles
+                b0 = dp4a_ss(qh[i] & 0x01010101u, a[i], b0);
+                b1 = dp4a_ss(qh[i] & 0x02020202u, a[8 + i], b1);              // 2 x the bits
+            }
+        }
+        {
+            const uint4 q2 = lds128(qsp + 32), q3 = lds128(qsp + 48);
+            const uint32_t qb[8] = {q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                g2 = dp4a_ss(qb[i] & 0x0f0f0f0fu, a[16 + i], g2);
+                g3 = dp4a_us(qb[i] & 0xf0f0f0f0u, a[24 + i], g3);
+                b2 = dp4a_ss(qh[i] & 0x04040404u, a[16 + i], b2);             // 4 x
+                b3 = dp4a_ss(qh[i] & 0x08080808u, a[24 + i], b3);             // 8 x
+            }
+        }
+        // |dot * sc| reaches 32 * 31 * 127 * 63 = 7.9 M: past the 2^22 of the mantissa trick, so the conversion instruction
+        float fd = d8.x * (float)((g0 + (b0 << 4)) * byte_of<0>(sc));
+        fd = fmaf(d8.y, (float)(((g1 >> 4) + (b1 << 3)) * byte_of<1>(sc)), fd);
+        fd = fmaf(d8.z, (float)((g2 + (b2 << 2)) * byte_of<2>(sc)), fd);
+        fd = fmaf(d8.w, (float)(((g3 >> 4) + (b3 << 1)) * byte_of<3>(sc)), fd);
         float t = byte_to_f32<0>(mn) * ds.x;
         t = fmaf(byte_to_f32<1>(mn), ds.y, t);
         t = fmaf(byte_to_f32<2>(mn), ds.z, t);
@@ -631,7 +689,8 @@ int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, const vo
     // warps: 12; seven chunks (K = 28672) take 14 (Q4_K) or 7 (Q6_K: its 3360-byte stages leave room for one row lane only)
     // (Q4_K with a pre-launched image also takes 7 warps: beside a 14-warp CTA and the 12-warp neighbour no register bank has room
     // for a CTA of the pre-launch, beside a 7-warp one it has -- see "Registers")
-    const int nw = (p.C == 7) ? ((Q6 || image != nullptr) ? 7 : 14) : 12;
+    constexpr bool Q5 = TYPE == T_Q5_K;
+    const int nw = (p.C == 7) ? ((Q6 || Q5 || image != nullptr) ? 7 : 14) : 12;
     const bool full = p.nsb % 16 == 0;
     if (p.C > 7 || nw % p.C != 0 || p.row_bytes % 16 != 0 || (p.C == 7 && !full)) return 1;
     // Q6_K, K = 28672 with the fused SwiGLU activation: 7 warps x 2 CTAs would spend 4.6 us on the 28672 exponentials (70B block
@@ -679,17 +738,23 @@ int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, const vo
     int S = 4;
     while (S > 2 && p.off_slots + nw * S * stage_bytes > half_sm) S--;
     if (force_s == 3 && S > 3) S = 3;
-    // instantiated -- Q4_K: 12 warps x {3, 4} stages, 14 warps x {2, 3}, 7 warps x {3, 4}; Q6_K: 12 warps x 2, 7 warps x {2, 3}
-    if ((nw == 14 || (nw == 7 && Q6)) && S > 3) S = 3;
+    // instantiated -- Q4_K: 12 warps x {3, 4} stages, 14 warps x {2, 3}, 7 warps x {3, 4}; Q5_K: 12 warps x {2, 3}, 7 warps x {3, 4};
+    // Q6_K: 12 warps x 2, 7 warps x {2, 3}
+    if ((nw == 14 || (nw == 7 && Q6) || (nw == 12 && Q5)) && S > 3) S = 3;
     if (nw == 7 && !Q6 && S < 3) return 1;
     if (Q6 && nw == 12) S = 2;
-    if (!Q6 && nw == 12 && S < 3) return 1;
+    if (!Q6 && !Q5 && nw == 12 && S < 3) return 1;
     const int smem = p.off_slots + nw * S * stage_bytes;
     if (smem > half_sm) return 1;
     if (probe_only) return 2;
     if (p.early == 0 || p.early > S) p.early = 1;
     p.trace = ggb_mmvq_trace_slot();
-    if constexpr (Q6) {
+    if constexpr (Q5) {
+        if (nw == 7)
+            return S == 4 ? launch_cfg<TYPE, T, 4, true, 7>(p, grid, smem, cluster, stream) : launch_cfg<TYPE, T, 3, true, 7>(p, grid, smem, cluster, stream);
+        if (S == 3) return full ? launch_cfg<TYPE, T, 3, true, 12>(p, grid, smem, cluster, stream) : launch_cfg<TYPE, T, 3, false, 12>(p, grid, smem, cluster, stream);
+        return full ? launch_cfg<TYPE, T, 2, true, 12>(p, grid, smem, cluster, stream) : launch_cfg<TYPE, T, 2, false, 12>(p, grid, smem, cluster, stream);
+    } else if constexpr (Q6) {
         if (nw == 7)
             return S == 3 ? launch_cfg<TYPE, T, 3, true, 7>(p, grid, smem, cluster, stream) : launch_cfg<TYPE, T, 2, true, 7>(p, grid, smem, cluster, stream);
         return full ? launch_cfg<TYPE, T, 2, true, 12>(p, grid, smem, cluster, stream) : launch_cfg<TYPE, T, 2, false, 12>(p, grid, smem, cluster, stream);
@@ -725,6 +790,7 @@ int ggb_mmvq_rg_impl(const void *W, const void *X, void *Y, int type, int xy_dty
     if (!(ggb_sb::g_rg_mode & 1) || B != 1 || K % 256 != 0 || K > 28672 || (reinterpret_cast<uintptr_t>(W) & 15)) return 1;
     switch (type) {
         case T_Q4_K: return dispatch_dtype<T_Q4_K>(W, X, Y, xy_dtype, K, N, image, probe_only, stream);
+        case T_Q5_K: return (ggb_sb::g_rg_mode & (1 << 29)) == 0 ? dispatch_dtype<T_Q5_K>(W, X, Y, xy_dtype, K, N, image, probe_only, stream) : 1;   // (debug bit 29: ring kernel)
         case T_Q6_K: return (K % 2048 == 0 && (ggb_sb::g_rg_mode & (1 << 27)) == 0)        // (debug bit 27: Q6_K stays on the ring kernel)
                                 ? dispatch_dtype<T_Q6_K>(W, X, Y, xy_dtype, K, N, image, probe_only, stream) : 1;
         default: return 1;
@@ -737,7 +803,8 @@ int ggb_mmvq_rg_wants_image(int type, int64_t B, int64_t K, const void *x2) {
     //  Q4_K 24.0 vs 26.0 us (14 warps), Q6_K 34.5 vs 37.6 us (7 warps))
     (void)x2;
     if (!(ggb_sb::g_rg_mode & 1) || B != 1 || K != 28672) return 0;
-    return type == T_Q4_K ? ((ggb_sb::g_rg_mode >> 28) & 1) == 0 : (type == T_Q6_K && !(ggb_sb::g_rg_mode & (1 << 27)));   // (debug bits 27 / 28: off)
+    if (type == T_Q5_K) return (ggb_sb::g_rg_mode & (1 << 29)) == 0;
+    return type == T_Q4_K ? ((ggb_sb::g_rg_mode >> 28) & 1) == 0 : (type == T_Q6_K && !(ggb_sb::g_rg_mode & (1 << 27)));   // (debug bits 27 / 28 / 29: off)
 }
 int64_t ggb_mmvq_rg_image_bytes(int64_t K) { return ((K + 15) & ~(int64_t)15) + 2 * (K / 128) * 16; }
 
@@ -764,8 +831,8 @@ int launch_prequant(const void *X, int64_t K, void *image, cudaStream_t stream) 
 }  // namespace
 
 int ggb_mmvq_rg_prequant(const void *X, int type, int xy_dtype, int64_t K, void *image, cudaStream_t stream) {
-    if (type != T_Q6_K && type != T_Q4_K) return 1;
-    const bool q6 = type == T_Q6_K;
+    if (type != T_Q6_K && type != T_Q4_K && type != T_Q5_K) return 1;
+    const bool q6 = type == T_Q6_K;              // (Q4_K and Q5_K share the image: the second word is d8 * sum(q8))
     switch (xy_dtype) {
         case GGB_F32:  return q6 ? launch_prequant<T_Q6_K, float>(X, K, image, stream) : launch_prequant<T_Q4_K, float>(X, K, image, stream);
         case GGB_F16:  return q6 ? launch_prequant<T_Q6_K, __half>(X, K, image, stream) : launch_prequant<T_Q4_K, __half>(X, K, image, stream);
