@@ -1,5 +1,5 @@
 // mmvq_rg.cu -- batch-1 MMVQ with the q8_1 activations RESIDENT IN REGISTERS (Q4_K: K % 256 == 0, K <= 16384, 24576, 28672;
-// Q5_K: the same; Q6_K: K % 2048 == 0, the same row lengths).
+// Q5_K: the same; Q6_K: K % 2048 == 0, the same row lengths; Q3_K: K % 2048 == 0, K <= 24576).
 //
 // Same contract as the other MMVQ kernels (ggml_mul_mat_vec_a8 = quantize_row_q8_1_cuda + mul_mat_vec_q + vec_dot_q4_K_q8_1,
 // hf-kernels/ggml-kernels/ggml/ggml_kernel.cu:13-66,80-193; ggml/mmvq.cuh:2-38; ggml/vecdotq.cuh:266-327).
@@ -282,6 +282,58 @@ template <> struct RgOps<T_Q6_K> {
             const int t = (dot[j][0] - 32 * sq0) * s0 + (dot[j][1] - 32 * sq1) * s1;
             f = fmaf(d8v[j], (float)t, f);
         }
+        return d * f;
+    }
+};
+
+// ---- Q3_K: hmask[32] @0, qs[64] @32 (2-bit), 12 scale bytes @96 (sixteen 6-bit scales, one per 16 values), d @108; 110-byte
+// super-blocks, 2-byte aligned like Q6_K.  Value = d * (sc - 32) * (q2 + 4 * hbit - 4)   (dequantize.cuh:129-151,
+// vecdotq.cuh:235-268).  The item = half n: qs bytes 32 n .. 32 n + 31 hold four groups j at bit 2 j, hmask bit 4 n + j is the
+// group's high bit.  Neither is ever shifted into place: the group's plane is masked out where it lies (0x03030303 << 2 j of
+// the qs word, 0x01010101 << j of the pre-shifted hmask word), dp4a returns 4^j * sum(q2 * q8) and 2^j * sum(hbit * q8), and
+// one shift per 16-value sub-block undoes the factors; the -4 goes through the integer half-sums of the q8 quants.
+template <> struct RgOps<T_Q3_K> {
+    static constexpr int BS = 110;
+    __device__ __forceinline__ static uint32_t aux_word(float, int s_lo16, int s_hi16) { return ((uint32_t)s_lo16 & 0xffffu) | ((uint32_t)s_hi16 << 16); }
+    __device__ __forceinline__ static float item(uint32_t hp, const uint32_t (&a)[32], const float4 d8, const float4 ds, int h) {
+        const uint32_t sh = (hp & 2u) * 8u, al = hp & ~3u;
+        uint32_t S[3];
+        lds_words<3>(al + 96, sh, S);
+        const float d = ggb_h2f((uint16_t)lds16(hp + 108));
+        // the item's eight 6-bit scales, one per byte (before the -32): k = 0..3 in scA, 4..7 in scB (gguf-py quants.py:442-454)
+        const uint32_t s4 = 4u * (uint32_t)h;
+        const uint32_t scA = ((S[0] >> s4) & 0x0f0f0f0fu) | (((S[2] >> s4) & 0x03030303u) << 4);
+        const uint32_t scB = ((S[1] >> s4) & 0x0f0f0f0fu) | (((S[2] >> (s4 + 2)) & 0x03030303u) << 4);
+        const uint32_t sqv[4] = {__float_as_uint(ds.x), __float_as_uint(ds.y), __float_as_uint(ds.z), __float_as_uint(ds.w)};
+        int t[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int u = 0; u < 2; u++) {                               // the 16-value halves of the four groups: words 4u .. 4u + 3
+            uint32_t ql[4], hm[4];
+            lds_words<4>(al + 32 + 32 * h + 16 * u, sh, ql);
+            lds_words<4>(al + 16 * u, sh, hm);
+            int gq[4] = {0, 0, 0, 0}, gb[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                const uint32_t hw = hm[w] >> s4;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    gq[j] = dp4a_us(ql[w] & (0x03030303u << (2 * j)), a[8 * j + 4 * u + w], gq[j]);
+                    gb[j] = dp4a_ss(hw & (0x01010101u << j), a[8 * j + 4 * u + w], gb[j]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int k = 2 * j + u;                            // sub-block inside the item
+                const int sc = (int)(((k < 4 ? scA : scB) >> (8 * (k & 3))) & 0xffu) - 32;
+                const int sq = u ? (int)(int16_t)(sqv[j] >> 16) : (int)(int16_t)(sqv[j] & 0xffffu);
+                const int dot = (gq[j] >> (2 * j)) + ((gb[j] >> j) << 2) - 4 * sq;
+                t[j] += sc * dot;
+            }
+        }
+        float f = d8.x * (float)t[0];
+        f = fmaf(d8.y, (float)t[1], f);
+        f = fmaf(d8.z, (float)t[2], f);
+        f = fmaf(d8.w, (float)t[3], f);
         return d * f;
     }
 };
@@ -690,6 +742,8 @@ int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, const vo
     // (Q4_K with a pre-launched image also takes 7 warps: beside a 14-warp CTA and the 12-warp neighbour no register bank has room
     // for a CTA of the pre-launch, beside a 7-warp one it has -- see "Registers")
     constexpr bool Q5 = TYPE == T_Q5_K;
+    constexpr bool Q3 = TYPE == T_Q3_K;
+    if (Q3 && p.C == 7) return 1;                       // (not instantiated for 7 chunks: the generic kernel keeps K = 28672)
     const int nw = (p.C == 7) ? ((Q6 || Q5 || image != nullptr) ? 7 : 14) : 12;
     const bool full = p.nsb % 16 == 0;
     if (p.C > 7 || nw % p.C != 0 || p.row_bytes % 16 != 0 || (p.C == 7 && !full)) return 1;
@@ -749,7 +803,10 @@ int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, const vo
     if (probe_only) return 2;
     if (p.early == 0 || p.early > S) p.early = 1;
     p.trace = ggb_mmvq_trace_slot();
-    if constexpr (Q5) {
+    if constexpr (Q3) {
+        if (S >= 4) return full ? launch_cfg<TYPE, T, 4, true, 12>(p, grid, smem, cluster, stream) : launch_cfg<TYPE, T, 4, false, 12>(p, grid, smem, cluster, stream);
+        return full ? launch_cfg<TYPE, T, 3, true, 12>(p, grid, smem, cluster, stream) : launch_cfg<TYPE, T, 3, false, 12>(p, grid, smem, cluster, stream);
+    } else if constexpr (Q5) {
         if (nw == 7)
             return S == 4 ? launch_cfg<TYPE, T, 4, true, 7>(p, grid, smem, cluster, stream) : launch_cfg<TYPE, T, 3, true, 7>(p, grid, smem, cluster, stream);
         if (S == 3) return full ? launch_cfg<TYPE, T, 3, true, 12>(p, grid, smem, cluster, stream) : launch_cfg<TYPE, T, 3, false, 12>(p, grid, smem, cluster, stream);
@@ -790,6 +847,8 @@ int ggb_mmvq_rg_impl(const void *W, const void *X, void *Y, int type, int xy_dty
     if (!(ggb_sb::g_rg_mode & 1) || B != 1 || K % 256 != 0 || K > 28672 || (reinterpret_cast<uintptr_t>(W) & 15)) return 1;
     switch (type) {
         case T_Q4_K: return dispatch_dtype<T_Q4_K>(W, X, Y, xy_dtype, K, N, image, probe_only, stream);
+        case T_Q3_K: return (K % 2048 == 0 && (ggb_sb::g_rg_mode & (1 << 30)) == 0)        // (debug bit 30: generic kernel)
+                                ? dispatch_dtype<T_Q3_K>(W, X, Y, xy_dtype, K, N, image, probe_only, stream) : 1;
         case T_Q5_K: return (ggb_sb::g_rg_mode & (1 << 29)) == 0 ? dispatch_dtype<T_Q5_K>(W, X, Y, xy_dtype, K, N, image, probe_only, stream) : 1;   // (debug bit 29: ring kernel)
         case T_Q6_K: return (K % 2048 == 0 && (ggb_sb::g_rg_mode & (1 << 27)) == 0)        // (debug bit 27: Q6_K stays on the ring kernel)
                                 ? dispatch_dtype<T_Q6_K>(W, X, Y, xy_dtype, K, N, image, probe_only, stream) : 1;
