@@ -1,5 +1,5 @@
 // mmvq_rg.cu -- batch-1 MMVQ with the q8_1 activations RESIDENT IN REGISTERS (Q4_K: K % 256 == 0, K <= 16384, 24576, 28672;
-// Q5_K: the same; Q6_K: K % 2048 == 0, the same row lengths; Q3_K: K % 2048 == 0, K <= 24576).
+// Q5_K: the same; Q6_K: K % 2048 == 0, the same row lengths; Q3_K: K % 2048 == 0, K <= 24576; Q2_K: K % 1024 == 0, K <= 24576).
 //
 // Same contract as the other MMVQ kernels (ggml_mul_mat_vec_a8 = quantize_row_q8_1_cuda + mul_mat_vec_q + vec_dot_q4_K_q8_1,
 // hf-kernels/ggml-kernels/ggml/ggml_kernel.cu:13-66,80-193; ggml/mmvq.cuh:2-38; ggml/vecdotq.cuh:266-327).
@@ -27,7 +27,7 @@
 
 namespace ggb_sb {
 extern int g_pdl_prefetch;
-int g_rg_mode = 1;           // ggb_set_option(GGB_OPT_MMVQ_RG): bit 0 = use this kernel; bits 8.. = debug (1 = skip quantization); bits 16..19 early stages; bits 20..27 rows pulled into L2 up front
+int g_rg_mode = 1;           // ggb_set_option(GGB_OPT_MMVQ_RG): bit 0 = use this kernel; bits 8.. = debug (1 = skip quantization); bits 12..15 stages, 16..19 early stages, 20..23 cluster size, 24..25 cluster policy, 26 plain launches, 27..31 one type each back on its previous kernel
 }
 unsigned long long *ggb_mmvq_trace_slot();
 
@@ -335,6 +335,46 @@ template <> struct RgOps<T_Q3_K> {
         f = fmaf(d8.z, (float)t[2], f);
         f = fmaf(d8.w, (float)t[3], f);
         return d * f;
+    }
+};
+
+// ---- Q2_K: 16 scale bytes @0 (4-bit scale | 4-bit minimum, one per 16 values), qs[64] @16 (2-bit), d @80, dmin @82; 84-byte
+// super-blocks are 4-byte aligned.  Value = d * sc * q2 - dmin * m   (dequantize.cuh:107-120, vecdotq.cuh:203-231).  The item = half n:
+// qs bytes 32 n .. 32 n + 31, group j at bit 2 j (masked in place: dp4a returns 4^j * sum(q2 * q8)), scale byte 8 n + 2 j + u for
+// the 16-value half u; the minima go through the integer half-sums of the q8 quants.
+template <> struct RgOps<T_Q2_K> {
+    static constexpr int BS = 84;
+    __device__ __forceinline__ static uint32_t aux_word(float, int s_lo16, int s_hi16) { return ((uint32_t)s_lo16 & 0xffffu) | ((uint32_t)s_hi16 << 16); }
+    __device__ __forceinline__ static float item(uint32_t hp, const uint32_t (&a)[32], const float4 d8, const float4 ds, int h) {
+        const uint32_t S0 = lds32(hp + 8 * h), S1 = lds32(hp + 8 * h + 4);
+        const uint32_t dmw = lds32(hp + 80);
+        const float2 dm = __half22float2(*reinterpret_cast<const __half2 *>(&dmw));
+        const uint32_t sqv[4] = {__float_as_uint(ds.x), __float_as_uint(ds.y), __float_as_uint(ds.z), __float_as_uint(ds.w)};
+        int ts[4] = {0, 0, 0, 0}, tm[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            uint32_t ql[4];
+#pragma unroll
+            for (int w = 0; w < 4; w++) ql[w] = lds32(hp + 16 + 32 * h + 16 * u + 4 * w);
+            int gq[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int w = 0; w < 4; w++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) gq[j] = dp4a_us(ql[w] & (0x03030303u << (2 * j)), a[8 * j + 4 * u + w], gq[j]);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int k = 2 * j + u;
+                const uint32_t sb = ((k < 4 ? S0 : S1) >> (8 * (k & 3))) & 0xffu;
+                const int sq = u ? (int)(int16_t)(sqv[j] >> 16) : (int)(int16_t)(sqv[j] & 0xffffu);
+                ts[j] += (int)(sb & 0xfu) * (gq[j] >> (2 * j));
+                tm[j] += (int)(sb >> 4) * sq;
+            }
+        }
+        float fs = d8.x * (float)ts[0], fm = d8.x * (float)tm[0];
+        fs = fmaf(d8.y, (float)ts[1], fs); fm = fmaf(d8.y, (float)tm[1], fm);
+        fs = fmaf(d8.z, (float)ts[2], fs); fm = fmaf(d8.z, (float)tm[2], fm);
+        fs = fmaf(d8.w, (float)ts[3], fs); fm = fmaf(d8.w, (float)tm[3], fm);
+        return dm.x * fs - dm.y * fm;
     }
 };
 
@@ -742,7 +782,7 @@ int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, const vo
     // (Q4_K with a pre-launched image also takes 7 warps: beside a 14-warp CTA and the 12-warp neighbour no register bank has room
     // for a CTA of the pre-launch, beside a 7-warp one it has -- see "Registers")
     constexpr bool Q5 = TYPE == T_Q5_K;
-    constexpr bool Q3 = TYPE == T_Q3_K;
+    constexpr bool Q3 = TYPE == T_Q3_K || TYPE == T_Q2_K;      // (the two 2-bit-plane types share the launch table)
     if (Q3 && p.C == 7) return 1;                       // (not instantiated for 7 chunks: the generic kernel keeps K = 28672)
     const int nw = (p.C == 7) ? ((Q6 || Q5 || image != nullptr) ? 7 : 14) : 12;
     const bool full = p.nsb % 16 == 0;
@@ -847,6 +887,8 @@ int ggb_mmvq_rg_impl(const void *W, const void *X, void *Y, int type, int xy_dty
     if (!(ggb_sb::g_rg_mode & 1) || B != 1 || K % 256 != 0 || K > 28672 || (reinterpret_cast<uintptr_t>(W) & 15)) return 1;
     switch (type) {
         case T_Q4_K: return dispatch_dtype<T_Q4_K>(W, X, Y, xy_dtype, K, N, image, probe_only, stream);
+        case T_Q2_K: return (K % 1024 == 0 && (ggb_sb::g_rg_mode & (1u << 31)) == 0)       // (84-byte super-blocks: rows and chunks 16-byte aligned every 4; debug bit 31: off)
+                                ? dispatch_dtype<T_Q2_K>(W, X, Y, xy_dtype, K, N, image, probe_only, stream) : 1;
         case T_Q3_K: return (K % 2048 == 0 && (ggb_sb::g_rg_mode & (1 << 30)) == 0)        // (debug bit 30: generic kernel)
                                 ? dispatch_dtype<T_Q3_K>(W, X, Y, xy_dtype, K, N, image, probe_only, stream) : 1;
         case T_Q5_K: return (ggb_sb::g_rg_mode & (1 << 29)) == 0 ? dispatch_dtype<T_Q5_K>(W, X, Y, xy_dtype, K, N, image, probe_only, stream) : 1;   // (debug bit 29: ring kernel)
@@ -861,7 +903,7 @@ int ggb_mmvq_rg_wants_image(int type, int64_t B, int64_t K, const void *x2) {
     // (plain rows too: measured on the 70B down projection, 7 warps behind the pre-launch vs the in-kernel pair quantization:
     //  Q4_K 24.0 vs 26.0 us (14 warps), Q6_K 34.5 vs 37.6 us (7 warps))
     (void)x2;
-    if (!(ggb_sb::g_rg_mode & 1) || B != 1 || K != 28672) return 0;
+    if (!(ggb_sb::g_rg_mode & 1) || B != 1 || (K != 28672 && !(K == 14336 && ((ggb_sb::g_rg_mode >> 8) & 2)))) return 0;   // (debug bit 9: K = 14336 too)
     if (type == T_Q5_K) return (ggb_sb::g_rg_mode & (1 << 29)) == 0;
     return type == T_Q4_K ? ((ggb_sb::g_rg_mode >> 28) & 1) == 0 : (type == T_Q6_K && !(ggb_sb::g_rg_mode & (1 << 27)));   // (debug bits 27 / 28 / 29: off)
 }
