@@ -903,7 +903,10 @@ int ggb_mmvq_rg_wants_image(int type, int64_t B, int64_t K, const void *x2) {
     // (plain rows too: measured on the 70B down projection, 7 warps behind the pre-launch vs the in-kernel pair quantization:
     //  Q4_K 24.0 vs 26.0 us (14 warps), Q6_K 34.5 vs 37.6 us (7 warps))
     (void)x2;
-    if (!(ggb_sb::g_rg_mode & 1) || B != 1 || (K != 28672 && !(K == 14336 && ((ggb_sb::g_rg_mode >> 8) & 2)))) return 0;   // (debug bit 9: K = 14336 too)
+    // rows of K >= 12288 (measured with / without: K = 14336 Q4_K 9.03 / 9.72 us, Q6_K 13.7 / 14.1; K = 28672 see above); debug bit 9:
+    // from K = 8192
+    const int64_t min_k = ((ggb_sb::g_rg_mode >> 8) & 2) ? 8192 : 12288;
+    if (!(ggb_sb::g_rg_mode & 1) || B != 1 || K < min_k || K > 28672) return 0;
     if (type == T_Q5_K) return (ggb_sb::g_rg_mode & (1 << 29)) == 0;
     return type == T_Q4_K ? ((ggb_sb::g_rg_mode >> 28) & 1) == 0 : (type == T_Q6_K && !(ggb_sb::g_rg_mode & (1 << 27)));   // (debug bits 27 / 28 / 29: off)
 }

@@ -184,6 +184,37 @@ def test_fused_swiglu_mlp_block_single_gpu(ops, dtype):
     assert torch.equal(y, ops.ggml_mul_mat_vec_a8(down.W, h, oracle.Q6_K, hidden))
 
 
+K_QUANTS = (oracle.Q2_K, oracle.Q3_K, oracle.Q4_K, oracle.Q5_K, oracle.Q6_K)
+
+
+@pytest.mark.parametrize("K", [2048, 6144, 8192, 12288, 14336, 16384, 24576, 28672])
+@pytest.mark.parametrize("t", K_QUANTS, ids=[oracle.TYPE_NAMES[t] for t in K_QUANTS])
+def test_register_kernel_row_lengths(ops, t, K):
+    """batch 1 of every K-quant on the register-resident kernel (mmvq_rg.cu): one chunk, whole and ragged chunks (K = 6144: 16 + 8
+    super-blocks; 14336: 16 + 16 + 16 + 8), two to seven chunks per row (12, 14 and 7 warps), the pre-launched activation image of
+    K = 28672; N chosen so that CTAs own 0, 1 and several rows."""
+    for N, dtype in ((77, torch.float16), (300, torch.float32)):
+        _check(ops, t, N, K, 1, dtype, seed=K // 256 + N)
+
+
+@pytest.mark.parametrize("t", (oracle.Q4_K, oracle.Q5_K, oracle.Q6_K), ids=["Q4_K", "Q5_K", "Q6_K"])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16], ids=["f16", "bf16"])
+def test_fused_swiglu_70b_down_projection(ops, t, dtype):
+    """the 70B down projection's row length (K = 28672) with the fused SwiGLU activation: 7 warps behind the 128-thread activation
+    pre-launch (mmvq_rg_prequant_kernel) -- bit-identical to the plain op on silu(g) * u computed by torch, batch 1 and 2."""
+    inter, hidden = 28672, 264
+    w = torch.from_numpy(oracle.random_weights(t, hidden, inter, seed=t)).cuda()
+    for B in (1, 2):
+        g = (torch.randn(B, inter, generator=torch.Generator().manual_seed(3 + B)) * 0.5).to(dtype).cuda()
+        u = (torch.randn(B, inter, generator=torch.Generator().manual_seed(5 + B)) * 0.5).to(dtype).cuda()
+        h = torch.nn.functional.silu(g) * u
+        y = torch.full((B, hidden), 7.0, dtype=dtype, device="cuda")
+        ops.mul_mat_vec_a8_fused(w, g, u, t, hidden, [y.data_ptr()], hidden, 0)
+        want = ops.ggml_mul_mat_vec_a8(w, h, t, hidden)
+        assert torch.equal(y, want), f"{oracle.TYPE_NAMES[t]} B={B} {dtype}: max diff {(y.float() - want.float()).abs().max().item()}"
+        _ = oracle  # the plain op itself is checked against the oracle at this row length in test_register_kernel_row_lengths
+
+
 def test_linearity_property(ops):
     """size-independent property at full size: rows of Y are independent, so a row-slice of W gives the
     same values as the slice of the full result (bit-for-bit: same K order per row)."""
