@@ -493,6 +493,121 @@ template <> struct MmaOps<T_Q6_K> {
 };
 
 
+// ---- Q2_K and Q3_K (round 2): the 2-bit formats on the Q6_K scheme -- one m16n8k16 u8 x s8 MMA per 16-value sub-block, the
+// per-sub-block factors as integers, minima / offsets through the tf32 MMA on the S16 table (32 * d8 * sum q8 per sub-block).
+//   Q2_K: scales[16] @0 (4-bit scale | 4-bit minimum), qs[64] @16, d @80, dmin @82 (84-byte super-blocks, 4-byte aligned):
+//         d * sum_k sc_k * dot_k  -  dmin * sum_k m_k * (d8 * sum q8)_k              (dequantize.cuh:107-120, vecdotq.cuh:203-231)
+//   Q3_K: hmask[32] @0, qs[64] @32, 12 scale bytes @96, d @108 (110-byte super-blocks, 2-byte aligned): weights q2 | hbit << 2 in
+//         0..7, d * sum_k (sc_k - 32) * (dot_k - 4 * sum q8_k)                      (dequantize.cuh:129-151, vecdotq.cuh:235-268)
+// Lane t owns bytes 4t..4t+3 of every 16-byte run; half ip = values 128 ip .., group j at bit 2 j of the qs byte.
+template <int TYPE, bool AL>
+__device__ __forceinline__ void q23_step(const uint8_t *r0, const uint8_t *r1, const uint8_t *ap, const float2 *dp,
+                                         const float2 *sp, int t, float (&acc)[4]) {
+    constexpr bool Q2 = TYPE == T_Q2_K;
+    constexpr int QS = Q2 ? 16 : 32;
+    const uint8_t *rr[2] = {r0, r1};
+    const uint32_t sh_t = 8u * t;
+    float cm[4] = {0.0f, 0.0f, 0.0f, 0.0f}, fs[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int ip = 0; ip < 2; ip++) {
+        int sc[2][8];
+        uint32_t a_lo[2], a_hi[2];
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            uint32_t w0, w1;                                   // the half's eight sub-block bytes (Q2_K: scale | min << 4; Q3_K: 6-bit scale)
+            if constexpr (Q2) {
+                w0 = ldw_a2<true>(rr[r] + 8 * ip);
+                w1 = ldw_a2<true>(rr[r] + 8 * ip + 4);
+            } else {
+                const uint32_t S0 = ldw_a2<AL>(rr[r] + 96), S1 = ldw_a2<AL>(rr[r] + 100), S2 = ldw_a2<AL>(rr[r] + 104);
+                w0 = ((S0 >> (4 * ip)) & 0x0f0f0f0fu) | (((S2 >> (4 * ip)) & 0x03030303u) << 4);
+                w1 = ((S1 >> (4 * ip)) & 0x0f0f0f0fu) | (((S2 >> (4 * ip + 2)) & 0x03030303u) << 4);
+            }
+            int mb_lo, mb_hi;                                  // the tf32 factor of sub-blocks t and t + 4 (Q2_K: minimum; Q3_K: scale - 32)
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int b = (int)(((k < 4 ? w0 : w1) >> (8 * (k & 3))) & 0xffu);
+                sc[r][k] = Q2 ? (b & 0xf) : b - 32;
+            }
+            {
+                const int blo = (int)((w0 >> sh_t) & 0xffu), bhi = (int)((w1 >> sh_t) & 0xffu);
+                mb_lo = Q2 ? (blo >> 4) : blo - 32;
+                mb_hi = Q2 ? (bhi >> 4) : bhi - 32;
+            }
+            a_lo[r] = __float_as_uint((float)mb_lo);           // exact tf32 operands (|value| <= 32)
+            a_hi[r] = __float_as_uint((float)mb_hi);
+        }
+        {
+            const float2 sa = sp[8 * ip + t], sb = sp[8 * ip + t + 4];
+            mma_tf32(cm, a_lo[0], a_lo[1], a_hi[0], a_hi[1], __float_as_uint(sa.x), __float_as_uint(sb.x));
+            mma_tf32(cm, a_lo[0], a_lo[1], a_hi[0], a_hi[1], __float_as_uint(sa.y), __float_as_uint(sb.y));
+        }
+        uint32_t wq[2][2], wh[2][2];                           // [row][16-value half u]: this lane's 4 bytes of qs (and of hmask)
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                wq[r][u] = ldw_a2<Q2 ? true : AL>(rr[r] + QS + 32 * ip + 16 * u + 4 * t);
+                if constexpr (!Q2) wh[r][u] = ldw_a2<AL>(rr[r] + 16 * u + 4 * t) >> (4 * ip);
+            }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {                          // 32-value group 4 ip + j = sub-blocks 2 j, 2 j + 1 of this half
+            uint32_t a[2][2];
+#pragma unroll
+            for (int r = 0; r < 2; r++)
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    a[r][u] = (wq[r][u] >> (2 * j)) & 0x03030303u;
+                    if constexpr (!Q2) a[r][u] |= ((wh[r][u] >> j) & 0x01010101u) << 2;
+                }
+            const uint8_t *ab = ap + 16 * (8 * ip + 2 * j) + 4 * t;
+            const uint32_t ba = *reinterpret_cast<const uint32_t *>(ab), bb = *reinterpret_cast<const uint32_t *>(ab + 16);
+            int ca[4], cb[4];
+            mma_u8s8_k16(ca, a[0][0], a[1][0], ba);
+            mma_u8s8_k16(cb, a[0][1], a[1][1], bb);
+            const float2 d8 = dp[4 * ip + j];
+            fs[0] = fmaf(d8.x, __int2float_rn(ca[0] * sc[0][2 * j] + cb[0] * sc[0][2 * j + 1]), fs[0]);
+            fs[1] = fmaf(d8.y, __int2float_rn(ca[1] * sc[0][2 * j] + cb[1] * sc[0][2 * j + 1]), fs[1]);
+            fs[2] = fmaf(d8.x, __int2float_rn(ca[2] * sc[1][2 * j] + cb[2] * sc[1][2 * j + 1]), fs[2]);
+            fs[3] = fmaf(d8.y, __int2float_rn(ca[3] * sc[1][2 * j] + cb[3] * sc[1][2 * j + 1]), fs[3]);
+        }
+    }
+    if constexpr (Q2) {
+        // cm = sum_k m_k * 32 * (d8 * sum q8)_k
+        const uint32_t dm0 = ldw_a2<true>(r0 + 80), dm1 = ldw_a2<true>(r1 + 80);
+        const float d0 = ggb_h2f(dm0 & 0xffffu), d1 = ggb_h2f(dm1 & 0xffffu);
+        const float n0 = ggb_h2f(dm0 >> 16) * 0.03125f, n1 = ggb_h2f(dm1 >> 16) * 0.03125f;
+        acc[0] += d0 * fs[0] - n0 * cm[0];
+        acc[1] += d0 * fs[1] - n0 * cm[1];
+        acc[2] += d1 * fs[2] - n1 * cm[2];
+        acc[3] += d1 * fs[3] - n1 * cm[3];
+    } else {
+        // cm = sum_k (sc_k - 32) * 32 * (d8 * sum q8)_k; the offset is -4 per value: -4 / 32 = -1/8
+        const float d0 = ggb_h2f(ld_u16(r0 + 108)), d1 = ggb_h2f(ld_u16(r1 + 108));
+        acc[0] += d0 * (fs[0] - 0.125f * cm[0]);
+        acc[1] += d0 * (fs[1] - 0.125f * cm[1]);
+        acc[2] += d1 * (fs[2] - 0.125f * cm[2]);
+        acc[3] += d1 * (fs[3] - 0.125f * cm[3]);
+    }
+}
+template <> struct MmaOps<T_Q2_K> {
+    static constexpr int BS = 84;
+    static constexpr int SMODE = 1;
+    __device__ __forceinline__ static void step(const uint8_t *r0, const uint8_t *r1, const uint8_t *ap, const float2 *dp,
+                                                const float2 *sp, int *, int, int t, float (&acc)[4]) {
+        q23_step<T_Q2_K, true>(r0, r1, ap, dp, sp, t, acc);
+    }
+};
+template <> struct MmaOps<T_Q3_K> {
+    static constexpr int BS = 110;
+    static constexpr int SMODE = 1;
+    __device__ __forceinline__ static void step(const uint8_t *r0, const uint8_t *r1, const uint8_t *ap, const float2 *dp,
+                                                const float2 *sp, int *, int, int t, float (&acc)[4]) {
+        if ((reinterpret_cast<uintptr_t>(r0) & 2) == 0) q23_step<T_Q3_K, true>(r0, r1, ap, dp, sp, t, acc);     // warp-uniform
+        else q23_step<T_Q3_K, false>(r0, r1, ap, dp, sp, t, acc);
+    }
+};
+
 // ---- the legacy 32-value block types (round 2): eight blocks = one 256-value unit of the kernel, like IQ4_NL.  Lane t owns
 // values 4t..4t+3 (a0/a1) and 16+4t..16+4t+3 (a2/a3) of every block and the matching activation bytes.  Offsets and minima
 // go through block_q8_1.s = the fp16 sum of the raw inputs, as in the reference (vecdotq.cuh:45-162): SMODE 2.
@@ -934,7 +1049,12 @@ bool plan(MmaParams &p, int &smem, int NW, int cs, int P, int B, int K, int64_t 
     const int64_t ngr = (N + kRowsPerGroup - 1) / kRowsPerGroup;
     const int nrg_max = (int)((ngr + grid - 1) / grid) + 1;
     p.accy_rgs = (nrg_max + NT - 1) / NT;
-    p.off_slots = (p.off_accy + (P > 1 ? NT * p.accy_rgs * 32 * 16 : 0) + 127) & ~127;
+    // the carried sums of a phased walk get a FIXED reserve (32 row groups per CTA + rounding: up to 75 776 rows on 148 SMs), so
+    // which (P, warps, chunk, team) plan fits -- and with it the fp32 summation order -- depends on (type, batch, K) only, never
+    // on N or the grid: an N-shard and the full matrix take the same plan (round-1 advisor finding)
+    constexpr int kAccyReserveRgs = 32;
+    if (P > 1 && NT * p.accy_rgs > kAccyReserveRgs + NT) return false;
+    p.off_slots = (p.off_accy + (P > 1 ? (kAccyReserveRgs + NT) * 32 * 16 : 0) + 127) & ~127;
     const int bar_bytes = (kMaxSlots + 1) * 8;
     const int avail = max_smem - p.off_slots - bar_bytes - 128;
     if (avail <= 0) return false;
@@ -1065,7 +1185,8 @@ bool mma_applies(int type, int64_t B, int64_t K) {
     // the dp4a kernel's per-CTA activation quantization (3.3 us at K = 14336) costs more than the image kernel's launch
     const int64_t min_b = (g_min_batch == 3 && K > 8192) ? 2 : g_min_batch;
     const bool legacy = type == T_Q4_0 || type == T_Q4_1 || type == T_Q5_0 || type == T_Q5_1 || type == T_Q8_0;
-    return (type == T_Q4_K || type == T_Q5_K || type == T_Q6_K || type == T_IQ4_XS || type == T_IQ4_NL || legacy) && B >= min_b && B <= 8 &&
+    return (type == T_Q4_K || type == T_Q5_K || type == T_Q6_K || type == T_Q2_K || type == T_Q3_K || type == T_IQ4_XS || type == T_IQ4_NL || legacy) &&
+           B >= min_b && B <= 8 &&
            K % 256 == 0 && K <= (1 << 16);
 }
 
@@ -1081,14 +1202,14 @@ void ggb_mmvq_mma_tune(int cs, int s_log2_plus1, int min_batch) {
 // workspace for the activation image (0 when this path does not apply)
 int64_t ggb_mmvq_mma_workspace_bytes(int type, int64_t B, int64_t K) {
     if (!mma_applies(type, B, K)) return 0;
-    return act_layout((int)B, (int)K, type == T_Q6_K).total;
+    return act_layout((int)B, (int)K, type == T_Q6_K || type == T_Q2_K || type == T_Q3_K).total;
 }
 
 // returns GGB_OK / a negative status, or 1 when this path does not apply (the caller tries mmvq_sb.cu, then mmvq.cu)
 int ggb_mmvq_mma_impl(const void *W, const void *X, void *Y, int type, int xy_dtype, int64_t B, int64_t K, int64_t N,
                       void *ws, int64_t ws_bytes, cudaStream_t stream) {
     if (!mma_applies(type, B, K) || (reinterpret_cast<uintptr_t>(W) & 15)) return 1;
-    if (!ws || (reinterpret_cast<uintptr_t>(ws) & 15) || ws_bytes < act_layout((int)B, (int)K, type == T_Q6_K).total) return 1;
+    if (!ws || (reinterpret_cast<uintptr_t>(ws) & 15) || ws_bytes < act_layout((int)B, (int)K, type == T_Q6_K || type == T_Q2_K || type == T_Q3_K).total) return 1;
     int rc;
     switch (type) {
         case T_Q4_K: rc = dispatch_dtype<T_Q4_K>(W, X, Y, xy_dtype, B, K, N, ws, stream); break;
@@ -1096,6 +1217,8 @@ int ggb_mmvq_mma_impl(const void *W, const void *X, void *Y, int type, int xy_dt
         case T_Q6_K: rc = dispatch_dtype<T_Q6_K>(W, X, Y, xy_dtype, B, K, N, ws, stream); break;
         case T_IQ4_XS: rc = dispatch_dtype<T_IQ4_XS>(W, X, Y, xy_dtype, B, K, N, ws, stream); break;
         case T_IQ4_NL: rc = dispatch_dtype<T_IQ4_NL>(W, X, Y, xy_dtype, B, K, N, ws, stream); break;
+        case T_Q2_K: rc = dispatch_dtype<T_Q2_K>(W, X, Y, xy_dtype, B, K, N, ws, stream); break;
+        case T_Q3_K: rc = dispatch_dtype<T_Q3_K>(W, X, Y, xy_dtype, B, K, N, ws, stream); break;
         case T_Q4_0: rc = dispatch_dtype<T_Q4_0>(W, X, Y, xy_dtype, B, K, N, ws, stream); break;
         case T_Q4_1: rc = dispatch_dtype<T_Q4_1>(W, X, Y, xy_dtype, B, K, N, ws, stream); break;
         case T_Q5_0: rc = dispatch_dtype<T_Q5_0>(W, X, Y, xy_dtype, B, K, N, ws, stream); break;

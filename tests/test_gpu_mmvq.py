@@ -184,6 +184,20 @@ def test_fused_swiglu_mlp_block_single_gpu(ops, dtype):
     assert torch.equal(y, ops.ggml_mul_mat_vec_a8(down.W, h, oracle.Q6_K, hidden))
 
 
+@pytest.mark.parametrize("case", [(oracle.Q4_K, 28672, 8), (oracle.Q6_K, 14336, 8), (oracle.Q4_K, 28672, 6)], ids=["Q4_K-K28672-B8", "Q6_K-K14336-B8", "Q4_K-K28672-B6"])
+def test_phased_walk_is_independent_of_n(ops, case):
+    """round-1 advisor finding: in the K-phased walk of the tensor-core kernel the plan (phases, warps, chunk, team) -- and with it
+    the fp32 summation order -- must not depend on N or the grid: a row shard gives the bits of the full matrix."""
+    t, K, B = case
+    N = 148 * 16 * 3 + 40
+    w = torch.from_numpy(oracle.random_weights(t, N, K, seed=B)).cuda()
+    x = torch.randn(B, K, generator=torch.Generator().manual_seed(1)).to(torch.float16).cuda()
+    full = ops.ggml_mul_mat_vec_a8(w, x, t, N)
+    for lo, hi in ((0, N // 8), (N // 2, N // 2 + 100), (N - 300, N)):
+        part = ops.ggml_mul_mat_vec_a8(w[lo:hi].contiguous(), x, t, hi - lo)
+        assert torch.equal(full[:, lo:hi], part), f"rows {lo}:{hi}"
+
+
 K_QUANTS = (oracle.Q2_K, oracle.Q3_K, oracle.Q4_K, oracle.Q5_K, oracle.Q6_K)
 
 
