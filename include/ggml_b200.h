@@ -68,7 +68,7 @@ enum ggb_option {
     GGB_OPT_MMQ_TILES = 3,     /* tuning/debug bits: 1 = one 256-token tile per weight stage, 2 = no clusters, 4 = no tail launch, 8 = no CTA-pair MMA (0 = automatic) */
     GGB_OPT_MMVQ_MMA = 5,      /* tuning/debug: super-blocks per chunk | (log2 K-split + 1) << 8 | minimum batch << 16 (0 fields = automatic) */
     GGB_OPT_MMVQ_TILED = 6,    /* tuning/debug: generic MMVQ kernel, largest TMA box in bytes for the tiled weight stages (0 = per-row bulk copies, -1 = default: per type, measured) */
-    GGB_OPT_MMVQ_PREQUANT = 8, /* MMVQ batches 1-2: the fused-SwiGLU activation of ggb_mmvq_fused (K >= 4096), and plain rows of at least this many values (default: none), take their q8_1 activation image from a pre-launch into the workspace instead of quantizing in every CTA; 0 = never */
+    GGB_OPT_MMVQ_PREQUANT = 8, /* MMVQ batches 1-2 on the ring kernels: the fused-SwiGLU activation of ggb_mmvq_fused (K >= 4096), and plain rows of at least this many values (default: none), take their q8_1 activation image from a pre-launch into the workspace instead of quantizing in every CTA; 0 = never.  (The batch-1 register kernel decides for itself: rows of K >= 12288 get their own 128-thread pre-launch, shorter ones quantize in-kernel, shared by a CTA pair.) */
     GGB_OPT_MMVQ_RG = 7,       /* tuning/debug: bit 0 = batch-1 kernels with register-resident activations (default 1); bit 1 = also for the types where the generic kernel measured faster; bits 8.. debug */
     GGB_OPT_MMVQ_L2_PREFETCH = 4 /* MB of weights per MMVQ launch pulled into L2 while the previous kernel drains (default 0 = off) */
 };
