@@ -346,9 +346,10 @@ def run_b200(args, rank, local_rank, world):
 
     # ---- e2e: the reference-named public ops (ggml.ggml_mul_mat_vec_a8 inside QuantMLP; every call allocates its output and
     # workspace), activations from pinned host memory and the result back to it inside the timed region, every step.
-    # N = 1: the step -- H2D copy, 80 x (gate, up, SwiGLU, down), D2H copy -- is captured ONCE with torch.cuda.graph and replayed,
-    # the way decode serving drives these ops (the copies are graph nodes: every replay moves the bytes); the eager number
-    # (Python + dispatcher bound: ~320 op calls per step) is reported beside it.  N > 1 stays eager (NCCL all-gathers).
+    # The step -- H2D copy, 80 x (gate, up, SwiGLU, down [+ NCCL all-gathers at N > 1]), D2H copy -- is captured ONCE with
+    # torch.cuda.graph and replayed, the way decode serving drives these ops (the copies are graph nodes: every replay moves the
+    # bytes); the eager number (Python + dispatcher bound: ~320 op calls per step) is reported beside it.  All ranks take the
+    # graph or none does.
     y_host = torch.empty(1, HIDDEN, dtype=torch.float16).pin_memory()
 
     def e2e_eager_step():
@@ -373,35 +374,47 @@ def run_b200(args, rank, local_rank, world):
     y_eager = y_host.clone()
     launches += 3 * n_layers * (e2e_steps + 1)
     e2e_s, e2e_how = e2e_eager_s, "eager torch ops"
-    if world == 1:
-        try:
-            s2 = torch.cuda.Stream()
-            s2.wait_stream(torch.cuda.current_stream())
+
+    def all_agree(ok: bool) -> bool:            # every rank takes the graph or none does (a rank that failed must not leave the others in a collective)
+        if world == 1:
+            return ok
+        f = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(f, op=dist.ReduceOp.MIN)
+        return bool(f.item())
+
+    g2, cap_err = None, ""
+    s2 = torch.cuda.Stream()
+    s2.wait_stream(torch.cuda.current_stream())
+    try:
+        with torch.cuda.stream(s2):
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2, stream=s2):
+                xd = x_host.to(dev, non_blocking=True)
+                y = None
+                for m in plain:
+                    y = m(xd)
+                y_host.copy_(y, non_blocking=True)
+    except Exception as e:                        # capture not possible here: the eager number stands
+        g2, cap_err = None, type(e).__name__
+        torch.cuda.synchronize()
+    if all_agree(g2 is not None):
+        def e2e_graph_step():
             with torch.cuda.stream(s2):
-                g2 = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g2, stream=s2):
-                    xd = x_host.to(dev, non_blocking=True)
-                    y = None
-                    for m in plain:
-                        y = m(xd)
-                    y_host.copy_(y, non_blocking=True)
-
-                def e2e_graph_step():
-                    g2.replay()
-                    torch.cuda.synchronize()
-
-                y_host.zero_()
-                e2e_graph_step()
-                if not torch.equal(y_host, y_eager):
-                    raise RuntimeError("graph replay of the e2e step differs from the eager result")
-                e2e_steps = max(e2e_steps, min(args.steps, 20))
-                e2e_s = timed(e2e_graph_step, e2e_steps)
-                e2e_how = "one torch.cuda.graph capture of the whole step (copies included), replayed per step"
-                launches += 3 * n_layers * (e2e_steps + 2)
-            torch.cuda.current_stream().wait_stream(s2)
-        except Exception as e:                    # capture not possible on this box: the eager number stands
-            e2e_how = f"eager torch ops (graph capture failed: {type(e).__name__})"
+                g2.replay()
             torch.cuda.synchronize()
+
+        y_host.zero_()
+        e2e_graph_step()
+        if all_agree(torch.equal(y_host, y_eager)):
+            e2e_steps = max(e2e_steps, min(args.steps, 20))
+            e2e_s = timed(e2e_graph_step, e2e_steps)
+            e2e_how = "one torch.cuda.graph capture of the whole step (copies" + (", NCCL all-gathers" if world > 1 else "") + " included), replayed per step"
+            launches += 3 * n_layers * (e2e_steps + 2)
+        else:
+            e2e_how = "eager torch ops (the graph replay differed from the eager result)"
+    elif cap_err or world > 1:
+        e2e_how = f"eager torch ops (graph capture failed on a rank: {cap_err or 'peer'})"
+    torch.cuda.current_stream().wait_stream(s2)
     if world > 1:
         tm = torch.tensor([e2e_s], device=dev)
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)

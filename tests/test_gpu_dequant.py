@@ -158,3 +158,22 @@ def test_reference_style_dequantize(ops, tmp_path, t, dtype, hidden_size):
         # and the stronger contract: the fused-dtype output is bit-identical to the cast of gguf-py's fp32
         fused = ops.ggml_dequantize(torch.tensor(tensor.data, device="cuda"), qt, *shape, dtype=dtype)
         assert torch.equal(fused, ref_output)
+
+
+@pytest.mark.parametrize("t", (oracle.Q4_0, oracle.Q4_K, oracle.Q6_K, oracle.IQ4_XS, oracle.IQ2_XS, oracle.IQ1_M),
+                         ids=lambda t: oracle.TYPE_NAMES[t])
+def test_static_weights_option_gives_the_same_bits(ops, t):
+    """GGB_OPT_STATIC_WEIGHTS = 1: the tile loads start before the previous kernel of the stream has finished; the values must
+    not change (back-to-back launches into different outputs)."""
+    m, n = 96, 2048
+    w = torch.from_numpy(oracle.random_weights(t, m, n, seed=t)).cuda()
+    want = ops.ggml_dequantize(w, t, m, n)
+    torch.cuda.synchronize()
+    ops.set_option(ops.GGB_OPT_STATIC_WEIGHTS, 1)
+    try:
+        got = [ops.ggml_dequantize(w, t, m, n) for _ in range(4)]
+        torch.cuda.synchronize()
+    finally:
+        ops.set_option(ops.GGB_OPT_STATIC_WEIGHTS, 0)
+    for g in got:
+        assert torch.equal(g, want)

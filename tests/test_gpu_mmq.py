@@ -213,3 +213,22 @@ def test_iq4_has_no_mmq(ops, t):
     w = torch.from_numpy(oracle.random_weights(t, 4, 512, seed=0)).cuda()
     with pytest.raises(ValueError):
         ops.ggml_mul_mat_a8(w, torch.zeros(16, 512, device="cuda"), t, 4)
+
+
+@pytest.mark.parametrize("case", [(oracle.Q4_K, 384, 2048, 83), (oracle.Q6_K, 256, 2048, 600), (oracle.Q4_0, 200, 1024, 128)],
+                         ids=["Q4_K-M83", "Q6_K-M600", "Q4_0-M128"])
+def test_static_weights_option_gives_the_same_bits(ops, case):
+    """GGB_OPT_STATIC_WEIGHTS = 1: the weight tiles of a launch start loading before the previous kernel has finished; same bits."""
+    t, N, K, M = case
+    w = torch.from_numpy(oracle.random_weights(t, N, K, seed=M)).cuda()
+    xs = [(torch.randn(M, K, generator=torch.Generator().manual_seed(i)) * 0.25).to(torch.float16).cuda() for i in range(3)]
+    want = [ops.ggml_mul_mat_a8(w, x, t, N) for x in xs]
+    torch.cuda.synchronize()
+    ops.set_option(ops.GGB_OPT_STATIC_WEIGHTS, 1)
+    try:
+        got = [ops.ggml_mul_mat_a8(w, x, t, N) for x in xs]
+        torch.cuda.synchronize()
+    finally:
+        ops.set_option(ops.GGB_OPT_STATIC_WEIGHTS, 0)
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)

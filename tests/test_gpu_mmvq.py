@@ -229,6 +229,31 @@ def test_fused_swiglu_70b_down_projection(ops, t, dtype):
         _ = oracle  # the plain op itself is checked against the oracle at this row length in test_register_kernel_row_lengths
 
 
+@pytest.mark.parametrize("case", [(oracle.Q4_K, 300, 4096, 1), (oracle.Q4_K, 200, 28672, 1), (oracle.Q6_K, 200, 28672, 1), (oracle.Q5_K, 150, 14336, 1),
+                                  (oracle.Q3_K, 300, 8192, 1), (oracle.Q2_K, 300, 4096, 1), (oracle.Q4_0, 300, 4096, 1), (oracle.IQ4_XS, 300, 4096, 2),
+                                  (oracle.Q4_K, 300, 4096, 5), (oracle.Q4_0, 300, 4096, 8), (oracle.Q2_K, 300, 4096, 4), (oracle.Q6_K, 70, 14336, 8),
+                                  (oracle.IQ2_XXS, 300, 4096, 1), (oracle.Q4_K, 300, 4096, 2)],
+                         ids=lambda c: f"{oracle.TYPE_NAMES[c[0]]}-{c[1]}x{c[2]}-B{c[3]}")
+def test_static_weights_option_gives_the_same_bits(ops, case):
+    """GGB_OPT_STATIC_WEIGHTS = 1 (what bench.py runs with) lets every kernel start its weight stream before the previous kernel of
+    the stream has finished.  It must not change a single bit: same kernels, same summation order.  Launches go back to back on
+    one stream so that the programmatic-dependent overlap really happens (the output of one call is not an input of the next,
+    exactly the situation the option is declared for)."""
+    t, N, K, B = case
+    w = torch.from_numpy(oracle.random_weights(t, N, K, seed=N + B)).cuda()
+    xs = [torch.randn(B, K, generator=torch.Generator().manual_seed(i)).to(torch.float16).cuda() for i in range(4)]
+    want = [ops.ggml_mul_mat_vec_a8(w, x, t, N) for x in xs]
+    torch.cuda.synchronize()
+    ops.set_option(ops.GGB_OPT_STATIC_WEIGHTS, 1)
+    try:
+        got = [ops.ggml_mul_mat_vec_a8(w, x, t, N) for x in xs]
+        torch.cuda.synchronize()
+    finally:
+        ops.set_option(ops.GGB_OPT_STATIC_WEIGHTS, 0)
+    for i, (a, b) in enumerate(zip(got, want)):
+        assert torch.equal(a, b), f"launch {i}: max diff {(a.float() - b.float()).abs().max().item()}"
+
+
 def test_linearity_property(ops):
     """size-independent property at full size: rows of Y are independent, so a row-slice of W gives the
     same values as the slice of the full result (bit-for-bit: same K order per row)."""
