@@ -187,3 +187,24 @@ def test_mmq_oracle_has_no_iq4():
     w = oracle.random_weights(oracle.IQ4_XS, 8, 512, seed=0)
     with pytest.raises(ValueError):
         oracle.mmq(w, oracle.IQ4_XS, np.zeros((2, 512), np.float32), 8)
+
+
+def test_iq_codebooks_are_pinned_to_gguf_py():
+    """The codebook tables of the product (csrc/iq_tables.cuh) and of the oracle (oracle/iq_tables.h) are generated files: both must
+    hold exactly what scripts/gen_iq_tables.py derives from gguf-py today (IQ3_S: with the reference's top level, see the
+    generator), entry for entry."""
+    import importlib.util
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_iq_tables", os.path.join(root, "scripts", "gen_iq_tables.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    for path in (os.path.join(root, "ggml-libtorch_b200", "csrc", "iq_tables.cuh"), os.path.join(root, "oracle", "iq_tables.h")):
+        txt = open(path).read()
+        for name, cls, remap in gen.TABLES:
+            want, _ = gen.grid_of(cls, remap)
+            m = re.search(r"%s\[(\d+)\]\s*=\s*\{(.*?)\};" % name, txt, re.S)
+            assert m, f"{name} missing in {path}"
+            got = np.array([int(v) for v in re.findall(r"(\d+)[uU]", m.group(2))], dtype=np.uint64)
+            assert int(m.group(1)) == len(want) and np.array_equal(got, want), f"{name} in {os.path.basename(path)}"
