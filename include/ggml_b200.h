@@ -114,11 +114,13 @@ int         ggb_quantize_q8_1(const void *X, int x_dtype, int64_t rows, int64_t 
  * MMVQ: Y[B, N] = q8_1(X[B, K]) . W[N, K]^T, 1 <= B <= 8 (the reference allows B == 1 only).
  * Replaces ggml_mul_mat_vec_a8 (ggml/ggml_kernel.cu:80-193): quantize_row_q8_1_cuda + mul_mat_vec_q
  * (ggml/mmvq.cuh:2-38).  X and Y share `xy_dtype`.
- * Launches: batches 1-2 (and every batch of the types without a tensor-core path) are ONE launch -- the activations are
- * quantized to q8_1 inside the GEMV kernel; batches 3-8 of Q4_K / Q5_K / Q6_K / IQ4_NL / IQ4_XS (2-8 for K > 8192) are TWO
- * programmatic-dependent launches: the q8_1 activation image is written once into `ws`, then the tensor-core GEMV reads
- * it (in-kernel it was repeated by all 148 CTAs).  `ws` must hold ggb_mmvq_workspace_bytes(type, B, K, N) bytes (0 for
- * the one-launch cases with K < 4096; a few KB otherwise); it is scratch: nothing survives the call.
+ * Launches: batches 1-2 (and every batch of the types without a tensor-core path: the codebook IQ formats) are ONE launch --
+ * the activations are quantized to q8_1 inside the GEMV kernel -- except batch 1 of the K-quants Q4_K / Q5_K / Q6_K on rows
+ * of K >= 12288, whose q8_1 activation image is written by a small pre-launch; batches 3-8 of Q2_K .. Q6_K, the five legacy
+ * types, IQ4_NL and IQ4_XS (2-8 for K > 8192) are TWO programmatic-dependent launches: the q8_1 activation image is written
+ * once into `ws`, then the tensor-core GEMV reads it (in-kernel it was repeated by all 148 CTAs).  `ws` must hold
+ * ggb_mmvq_workspace_bytes(type, B, K, N) bytes (0 for the one-launch cases with K < 4096; ~1.3 bytes per activation value
+ * otherwise); it is scratch: nothing survives the call.
  */
 int64_t     ggb_mmvq_workspace_bytes(int type, int64_t B, int64_t K, int64_t N);
 int         ggb_mmvq(const void *W, const void *X, void *Y, int type, int xy_dtype,
@@ -131,7 +133,8 @@ int         ggb_mmvq(const void *W, const void *X, void *Y, int type, int xy_dty
  * of one symmetric buffer [B, ldy] as mapped on every rank of the tensor-parallel group (NVLink peer mappings; its own
  * copy included), ldy = N_total and col_offset = rank * N, so each rank writes its slice into every rank's copy of the
  * full output.  The caller orders the exchange with a cross-rank barrier on the stream before the result is read.
- * Types Q4_K / Q5_K / Q6_K with K % 256 == 0 (Q6_K: K % 2048 == 0), 1 <= B <= 8; anything else returns GGB_E_SHAPE and
+ * Types Q4_K / Q5_K / Q6_K / IQ4_XS with K % 256 == 0 (Q6_K: K % 2048 == 0, IQ4_XS: K % 512 == 0), 1 <= B <= 8 (exactly
+ * ggb_mmvq_fused_supported); anything else returns GGB_E_SHAPE and
  * the caller uses ggb_mmvq + an all-gather.  Workspace: ggb_mmvq_workspace_bytes.
  */
 int         ggb_mmvq_gather(const void *W, const void *X, int type, int xy_dtype, int64_t B, int64_t K, int64_t N,
