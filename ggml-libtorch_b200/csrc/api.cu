@@ -29,6 +29,8 @@ int ggb_mmvq_mma_impl(const void *W, const void *X, void *Y, int type, int xy_dt
 int ggb_mmvq_sb_impl(const void *W, const void *X, void *Y, int type, int xy_dtype, int64_t B, int64_t K, int64_t N,
                      void *ws, int64_t ws_bytes, cudaStream_t stream);
 void ggb_mmvq_sb_set_prequant_min_k(int k);
+int ggb_moe_mmvq_impl(const void *W, const void *X, const int32_t *ids, void *Y, int type, int xy_dtype, int64_t tokens,
+                      int64_t top_k, int64_t n_experts, int64_t K, int64_t N, cudaStream_t stream);
 
 // ---------------------------------------------------------------- errors
 static thread_local char g_err[512] = "";
@@ -327,6 +329,29 @@ int ggb_mmvq(const void *W, const void *X, void *Y, int type, int xy_dtype, int6
         return GGB_E_ARG;
     }
     return ggb_mmvq_impl(W, X, Y, type, xy_dtype, B, K, N, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int ggb_moe_mmvq(const void *W, const void *X, const int32_t *topk_ids, void *Y, int type, int xy_dtype, int64_t tokens,
+                 int64_t top_k, int64_t n_experts, int64_t K, int64_t N, void *stream) {
+    g_err[0] = 0;
+    if (top_k < 1 || n_experts < 1 || tokens < 0 || tokens > ((int64_t)1 << 40) / top_k) {
+        ggb_set_error("ggb_moe_mmvq: need top_k >= 1, n_experts >= 1, tokens >= 0 (got %lld, %lld, %lld)", (long long)top_k,
+                      (long long)n_experts, (long long)tokens);
+        return GGB_E_SHAPE;
+    }
+    if (top_k > 65535 || n_experts > 0x7fffffff) {
+        ggb_set_error("ggb_moe_mmvq: top_k %lld / n_experts %lld out of range", (long long)top_k, (long long)n_experts);
+        return GGB_E_SHAPE;
+    }
+    const int rc = check_matmul("ggb_moe_mmvq", W, X, Y, type, xy_dtype, tokens, K, N);
+    if (rc < 0) return rc;
+    if (rc > 0) return GGB_OK;
+    if (!topk_ids || (reinterpret_cast<uintptr_t>(topk_ids) & 3)) {
+        ggb_set_error("ggb_moe_mmvq: topk_ids must be a 4-byte aligned device pointer to int32");
+        return GGB_E_ARG;
+    }
+    return ggb_moe_mmvq_impl(W, X, topk_ids, Y, type, xy_dtype, tokens, top_k, n_experts, K, N,
+                             static_cast<cudaStream_t>(stream));
 }
 
 int64_t ggb_mmq_workspace_bytes(int type, int64_t M, int64_t K, int64_t N) {

@@ -53,6 +53,15 @@ struct Params {
     int off_bars;
 };
 
+// Grouped (mixture-of-experts) launches only: blockIdx.y is one (token, expert) pair; see ggb_moe_mmvq_impl below.
+struct MoeParams {
+    const int32_t *ids;  // [pairs] expert of pair i (token i / top_k)
+    int64_t expert_stride;   // bytes between the [N, row_bytes] matrices of consecutive experts
+    int64_t ldy;         // elements between the output rows of consecutive pairs
+    int n_experts;
+    int top_k;
+};
+
 // ---------------------------------------------------------------- per-type traits
 }  // namespace
 #include "mmvq_group_ops.cuh"
@@ -60,9 +69,8 @@ namespace {
 using namespace ggb_group;
 
 // ---------------------------------------------------------------- the kernel
-template <int TYPE, int B, typename T>
-__global__ void __launch_bounds__(kThreads, 1)
-mmvq_kernel(const Params p, const __grid_constant__ CUtensorMap tmapW) {
+template <int TYPE, int B, typename T, bool MOE>
+__device__ __forceinline__ void mmvq_body(const Params &p, const CUtensorMap &tmapW, const MoeParams &moe) {
     extern __shared__ __align__(128) uint8_t smem[];
     int8_t *act_q = reinterpret_cast<int8_t *>(smem);                          // [B][K]
     float2 *act_s = reinterpret_cast<float2 *>(smem + p.off_scales);           // [B][K/32] {d8, aux}
@@ -80,6 +88,23 @@ mmvq_kernel(const Params p, const __grid_constant__ CUtensorMap tmapW) {
     const int nrows = (int)(r_end - r_begin);
     const int nrgroups = (nrows + kStageRows - 1) / kStageRows;
 
+    // grouped launch: this CTA's pair selects the expert's matrix, the token's activation row and the output row
+    const uint8_t *Wbase = p.W;
+    const T *Xrow = static_cast<const T *>(p.X);
+    T *Y = static_cast<T *>(p.Y);
+    if constexpr (MOE) {
+        const int pair = blockIdx.y;
+        const int e = moe.ids[pair];
+        Y += (int64_t)pair * moe.ldy;
+        if (e < 0 || e >= moe.n_experts) {
+            // an id outside [0, E) (padding / an expert held by another rank): the pair's output row is zero
+            for (int i = tid; i < nrows; i += kThreads) Y[r_begin + i] = from_f32<T>(0.0f);
+            return;
+        }
+        Wbase += (int64_t)e * moe.expert_stride;
+        Xrow += (int64_t)(pair / moe.top_k) * K;
+    }
+
     if (tid == 0) {
         for (int s = 0; s < p.nstages; s++) {
             mbar_init(&full[s], 1);
@@ -95,7 +120,7 @@ mmvq_kernel(const Params p, const __grid_constant__ CUtensorMap tmapW) {
         int it = 0;
         for (int rg = 0; rg < nrgroups; rg++) {
             const int nvalid = min(kStageRows, nrows - rg * kStageRows);
-            const uint8_t *wrow = p.W + (r_begin + (int64_t)rg * kStageRows) * p.row_bytes;
+            const uint8_t *wrow = Wbase + (r_begin + (int64_t)rg * kStageRows) * p.row_bytes;
             for (int c = 0; c < p.nchunks; c++, it++) {
                 const int s = it % p.nstages;
                 const uint32_t ph = (uint32_t)(it / p.nstages) & 1u;
@@ -133,7 +158,7 @@ mmvq_kernel(const Params p, const __grid_constant__ CUtensorMap tmapW) {
 
     // ===================== consumers: quantize the activations to q8_1 in shared memory =====================
     {
-        const T *X = static_cast<const T *>(p.X);
+        const T *X = Xrow;
         const int t4 = lane & 3;
         const int total = B * ngroups_row;                       // groups; 4 lanes each
         for (int base = 0; base < total; base += (kConsumerWarps * 32) / 4) {
@@ -168,7 +193,6 @@ mmvq_kernel(const Params p, const __grid_constant__ CUtensorMap tmapW) {
     }
 
     // ===================== consumers: stream stages, two rows per warp =====================
-    T *Y = static_cast<T *>(p.Y);
     int it = 0;
     for (int rg = 0; rg < nrgroups; rg++) {
         float acc[kRowsPerWarp][B];
@@ -234,6 +258,19 @@ mmvq_kernel(const Params p, const __grid_constant__ CUtensorMap tmapW) {
     }
 }
 
+template <int TYPE, int B, typename T>
+__global__ void __launch_bounds__(kThreads, 1)
+mmvq_kernel(const Params p, const __grid_constant__ CUtensorMap tmapW) {
+    mmvq_body<TYPE, B, T, false>(p, tmapW, MoeParams{});
+}
+
+// One launch for every (token, expert) pair of a mixture-of-experts layer: grid = (row ranges, pairs), batch 1 per CTA.
+template <int TYPE, typename T>
+__global__ void __launch_bounds__(kThreads, 1)
+moe_mmvq_kernel(const Params p, const __grid_constant__ CUtensorMap tmapW, const MoeParams moe) {
+    mmvq_body<TYPE, 1, T, true>(p, tmapW, moe);
+}
+
 // ---------------------------------------------------------------- host side
 int g_max_box = -1;          // GGB_OPT_MMVQ_TILED: largest TMA box (bytes) of the tiled stages; 0 = per-row bulk copies; -1 = per type
 
@@ -244,11 +281,12 @@ int g_max_box = -1;          // GGB_OPT_MMVQ_TILED: largest TMA box (bytes) of t
 // won (batch 1-2), per-row bulk copies elsewhere.
 template <int TYPE> constexpr bool kTiledByDefault = (TYPE == T_Q4_0 || TYPE == T_Q4_1 || TYPE == T_Q5_1 || TYPE == T_Q2_K);
 
-template <int TYPE, int B, typename T>
-int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, cudaStream_t stream) {
+// Stage geometry and shared-memory plan of one launch (shared by the plain and the grouped kernel).  Returns GGB_OK, an
+// error, or 1 when the B x K activations do not fit beside a 2-stage ring.
+template <int TYPE, int B>
+int plan_launch(Params &p, CUtensorMap &tmap, int &smem, const void *W, const void *X, void *Y, int64_t K, int64_t N,
+                bool allow_tiled, const DeviceInfo &di) {
     constexpr int QK = BlockTraits<TYPE>::QK, BS = BlockTraits<TYPE>::BS;
-    const DeviceInfo &di = ggb_device_info();
-    Params p;
     p.W = static_cast<const uint8_t *>(W);
     p.X = X;
     p.Y = Y;
@@ -264,7 +302,7 @@ int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, cudaStre
     // multiple of 16 bytes and at most 1024 (the TMA box limit of 256 uint32 elements); rows shorter than a chunk and
     // block sizes that do not split that way (Q6_K: 210 bytes) keep the per-row bulk copies
     p.nbox = p.box_bytes = p.gpb = 0;
-    const int max_box = g_max_box >= 0 ? g_max_box : ((kTiledByDefault<TYPE> && B <= 2) ? 1024 : 0);
+    const int max_box = !allow_tiled ? 0 : g_max_box >= 0 ? g_max_box : ((kTiledByDefault<TYPE> && B <= 2) ? 1024 : 0);
     if (p.fast && K >= kChunkElems && N <= 0x7fffffff) {
         for (int nb = 1; nb <= 8; nb *= 2) {
             const int bb = p.chunk_bytes / nb, gpb = kChunkGroups / nb;
@@ -276,7 +314,6 @@ int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, cudaStre
             }
         }
     }
-    alignas(64) CUtensorMap tmap;
     memset(&tmap, 0, sizeof tmap);
     if (p.nbox) {
         const int rc = ggb_make_row_tensor_map(&tmap, W, N, p.row_bytes, kStageRows, p.box_bytes, "ggb_mmvq");
@@ -294,7 +331,18 @@ int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, cudaStre
     if (nst > kMaxStages) nst = kMaxStages;
     p.nstages = nst;
     p.off_bars = (p.off_stages + nst * stage_bytes + 127) & ~127;
-    const int smem = p.off_bars + bar_bytes;
+    smem = p.off_bars + bar_bytes;
+    return GGB_OK;
+}
+
+template <int TYPE, int B, typename T>
+int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, cudaStream_t stream) {
+    const DeviceInfo &di = ggb_device_info();
+    Params p;
+    alignas(64) CUtensorMap tmap;
+    int smem = 0;
+    const int prc = plan_launch<TYPE, B>(p, tmap, smem, W, X, Y, K, N, true, di);
+    if (prc != GGB_OK) return prc;
 
     static bool attr_set[64] = {};               // per instantiation and device; idempotent, so a race is harmless
     if (!attr_set[di.dev]) {
@@ -307,6 +355,78 @@ int launch(const void *W, const void *X, void *Y, int64_t K, int64_t N, cudaStre
     mmvq_kernel<TYPE, B, T><<<grid, kThreads, smem, stream>>>(p, tmap);
     GGB_CUDA_TRY(cudaGetLastError());
     return GGB_OK;
+}
+
+// Grouped MMVQ for mixture-of-experts decode (no counterpart in the reference -- the op is
+// vLLM's ggml_moe_a8_vec): Y[i, :] = q8_1(X[i / top_k, :]) . W[ids[i]]^T for every pair i < pairs, ONE launch.  The
+// grid is (row ranges, pairs); a CTA quantizes its pair's activation row and streams its rows of the expert's matrix
+// through the same ring as the plain kernel (per-row bulk copies: a tiled tensor map would have to span the experts).
+// Pairs that share an expert stream its rows once each (they meet in L2 when they run together).
+template <int TYPE, typename T>
+int launch_moe(const void *W, const void *X, const int32_t *ids, void *Y, int64_t pairs, int64_t top_k, int64_t n_experts,
+               int64_t K, int64_t N, cudaStream_t stream) {
+    const DeviceInfo &di = ggb_device_info();
+    Params p;
+    alignas(64) CUtensorMap tmap;
+    int smem = 0;
+    const int prc = plan_launch<TYPE, 1>(p, tmap, smem, W, X, Y, K, N, false, di);
+    if (prc == 1) {
+        ggb_set_error("ggb_moe_mmvq: K=%lld is too large for one activation row in shared memory", (long long)K);
+        return GGB_E_SHAPE;
+    }
+    if (prc != GGB_OK) return prc;
+    MoeParams moe;
+    moe.expert_stride = N * (int64_t)p.row_bytes;
+    moe.ldy = N;
+    moe.n_experts = (int)n_experts;
+    moe.top_k = (int)top_k;
+    p.fast = p.fast && (moe.expert_stride % 16 == 0);
+
+    static bool attr_set[64] = {};
+    if (!attr_set[di.dev]) {
+        GGB_CUDA_TRY(cudaFuncSetAttribute(moe_mmvq_kernel<TYPE, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          di.max_smem_optin));
+        attr_set[di.dev] = true;
+    }
+    GGB_CUDA_TRY((ggb_prefer_max_smem_once<moe_mmvq_kernel<TYPE, T>>(di.dev)));
+    // gridDim.y is limited to 65535: whole tokens per launch
+    const int64_t per_launch = (65535 / top_k) * top_k;
+    for (int64_t p0 = 0; p0 < pairs; p0 += per_launch) {
+        const int64_t np = pairs - p0 < per_launch ? pairs - p0 : per_launch;
+        // row ranges per pair: the split that minimises (waves of CTAs) x (rows per CTA + the prologue's worth of rows)
+        int gx = 1;
+        {
+            const int64_t gx_max = N < 4 * di.sm_count ? N : 4 * di.sm_count;
+            double best = 1e300;
+            for (int64_t g = 1; g <= gx_max; g++) {
+                const int64_t waves = (g * np + di.sm_count - 1) / di.sm_count;
+                const double cost = (double)waves * ((double)((N + g - 1) / g) + 48.0);
+                if (cost < best) {
+                    best = cost;
+                    gx = (int)g;
+                }
+            }
+        }
+        p.X = static_cast<const T *>(X) + (p0 / top_k) * K;
+        p.Y = static_cast<T *>(Y) + p0 * N;
+        moe.ids = ids + p0;
+        moe_mmvq_kernel<TYPE, T><<<dim3(gx, (unsigned)np), kThreads, smem, stream>>>(p, tmap, moe);
+        GGB_CUDA_TRY(cudaGetLastError());
+    }
+    return GGB_OK;
+}
+
+template <int TYPE>
+int dispatch_moe_dtype(const void *W, const void *X, const int32_t *ids, void *Y, int dt, int64_t pairs, int64_t top_k,
+                       int64_t n_experts, int64_t K, int64_t N, cudaStream_t stream) {
+    switch (dt) {
+        case GGB_F32:  return launch_moe<TYPE, float>(W, X, ids, Y, pairs, top_k, n_experts, K, N, stream);
+        case GGB_F16:  return launch_moe<TYPE, __half>(W, X, ids, Y, pairs, top_k, n_experts, K, N, stream);
+        case GGB_BF16: return launch_moe<TYPE, __nv_bfloat16>(W, X, ids, Y, pairs, top_k, n_experts, K, N, stream);
+        default:
+            ggb_set_error("ggb_moe_mmvq: unknown dtype %d", dt);
+            return GGB_E_DTYPE;
+    }
 }
 
 template <int TYPE, typename T>
@@ -414,4 +534,24 @@ int ggb_mmvq_impl(const void *W, const void *X, void *Y, int type, int xy_dtype,
             ggb_set_error("ggb_mmvq: unsupported ggml type %d", type);
             return GGB_E_TYPE;
     }
+}
+
+int ggb_moe_mmvq_impl(const void *W, const void *X, const int32_t *ids, void *Y, int type, int xy_dtype, int64_t tokens,
+                      int64_t top_k, int64_t n_experts, int64_t K, int64_t N, cudaStream_t stream) {
+    if (K > (1 << 24)) {
+        ggb_set_error("ggb_moe_mmvq: K=%lld too large", (long long)K);
+        return GGB_E_SHAPE;
+    }
+    const int64_t pairs = tokens * top_k;
+#define GGB_MOE_CASE(TT) case TT: return dispatch_moe_dtype<TT>(W, X, ids, Y, xy_dtype, pairs, top_k, n_experts, K, N, stream)
+    switch (type) {
+        GGB_MOE_CASE(T_Q4_0); GGB_MOE_CASE(T_Q4_1); GGB_MOE_CASE(T_Q5_0); GGB_MOE_CASE(T_Q5_1); GGB_MOE_CASE(T_Q8_0);
+        GGB_MOE_CASE(T_Q2_K); GGB_MOE_CASE(T_Q3_K); GGB_MOE_CASE(T_Q4_K); GGB_MOE_CASE(T_Q5_K); GGB_MOE_CASE(T_Q6_K);
+        GGB_MOE_CASE(T_IQ4_NL); GGB_MOE_CASE(T_IQ4_XS); GGB_MOE_CASE(T_IQ2_XXS); GGB_MOE_CASE(T_IQ2_XS);
+        GGB_MOE_CASE(T_IQ2_S); GGB_MOE_CASE(T_IQ3_XXS); GGB_MOE_CASE(T_IQ3_S); GGB_MOE_CASE(T_IQ1_S); GGB_MOE_CASE(T_IQ1_M);
+        default:
+            ggb_set_error("ggb_moe_mmvq: unsupported ggml type %d", type);
+            return GGB_E_TYPE;
+    }
+#undef GGB_MOE_CASE
 }

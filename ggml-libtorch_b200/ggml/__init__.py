@@ -26,6 +26,7 @@ __all__ = [
     "set_option", "GGB_OPT_STATIC_WEIGHTS", "mul_mat_vec_a8_gather", "mul_mat_vec_a8_fused",
     "block_elems", "block_bytes", "SUPPORTED_TYPES", "MMQ_TYPES", "MMVQ_MAX_BATCH", "mmvq_fused_supported",
     "register_reference_namespace",
+    "ggml_moe_a8_vec", "ggml_moe_a8", "ggml_moe_get_block_size", "moe_a8_vec_out", "moe_align_block_size",
 ]
 
 _lib = _capi.lib
@@ -314,6 +315,128 @@ def ggml_mul_mat_vec_a8(W: torch.Tensor, X: torch.Tensor, quant_type: int, row: 
 def ggml_mul_mat_a8(W: torch.Tensor, X: torch.Tensor, quant_type: int, row: int) -> torch.Tensor:
     """Mulmat through the MMQ kernel for arbitrary batch size."""
     return torch.ops.ggml_b200.ggml_mul_mat_a8(W, X, int(quant_type), int(row))
+
+
+# ------------------------------------------------------------------------------------------------
+# mixture-of-experts variants (SURVEY.md section 8f rank 4).  Not in this reference; names, argument order and output
+# layout are those of its upstream's ops (vLLM `_custom_ops.ggml_moe_a8_vec / ggml_moe_a8 / ggml_moe_get_block_size`).
+# ------------------------------------------------------------------------------------------------
+
+def _check_experts(W: torch.Tensor, quant_type: int, row: int, K: int, what: str) -> int:
+    if W.dim() != 3:
+        raise ValueError(f"{what}: W must be the stacked expert weights [E, row, bytes_per_row]")
+    E = W.shape[0]
+    _check_w(W, quant_type, E * row, K, what)
+    return E
+
+
+def moe_a8_vec_out(X: torch.Tensor, W: torch.Tensor, topk_ids: torch.Tensor, top_k: int, quant_type: int, row: int,
+                   tokens: int, out: torch.Tensor) -> torch.Tensor:
+    """Grouped MMVQ (ggb_moe_mmvq): out[i] = q8_1(X[i // top_k]) . W[topk_ids.flatten()[i]]^T for i < tokens * top_k, one
+    launch, no allocation (`topk_ids` must already be int32), CUDA-graph capturable."""
+    what = "ggml_moe_a8_vec"
+    _check_x(X, W, what)
+    if X.dim() != 2 or X.shape[0] != tokens:
+        raise ValueError(f"{what}: X must be [tokens, K]")
+    K = X.shape[1]
+    E = _check_experts(W, quant_type, row, K, what)
+    pairs = tokens * top_k
+    if topk_ids.dtype != torch.int32 or not topk_ids.is_contiguous() or topk_ids.numel() != pairs or topk_ids.device != W.device:
+        raise ValueError(f"{what}: topk_ids must be a contiguous int32 tensor of tokens * top_k = {pairs} ids on W's device")
+    if out.dtype != X.dtype or not out.is_contiguous() or out.numel() != pairs * row or out.device != W.device:
+        raise ValueError(f"{what}: out must be a contiguous [tokens * top_k, row] tensor of X's dtype")
+    with torch.cuda.device(W.device):
+        rc = _lib.ggb_moe_mmvq(W.data_ptr(), X.data_ptr(), topk_ids.data_ptr(), out.data_ptr(), int(quant_type),
+                               _DT[X.dtype], tokens, top_k, E, K, row, _stream(W))
+    _capi.check(rc, what)
+    return out
+
+
+def ggml_moe_a8_vec(X: torch.Tensor, W: torch.Tensor, topk_ids: torch.Tensor, top_k: int, quant_type: int, row: int,
+                    tokens: int) -> torch.Tensor:
+    """MoE matmul through the grouped MMVQ kernel: X [tokens, K], W [E, row, bytes] raw GGUF expert stack, topk_ids
+    [tokens, top_k] -> [tokens * top_k, row] (row i = token i // top_k through expert topk_ids[i // top_k, i % top_k]).
+    The second projection of an expert MLP is the same call with top_k = 1 and tokens = the number of pairs."""
+    ids = topk_ids.reshape(-1)
+    if ids.dtype != torch.int32:
+        ids = ids.to(torch.int32)
+    out = torch.empty((int(tokens) * int(top_k), int(row)), dtype=X.dtype, device=W.device)
+    return moe_a8_vec_out(X, W, ids.contiguous(), int(top_k), int(quant_type), int(row), int(tokens), out)
+
+
+_MOE_BLOCK = 32
+
+
+def ggml_moe_get_block_size(quant_type: int) -> int:
+    """Padding granularity of the per-expert token lists `ggml_moe_a8` expects (upstream: the MMQ tile width per type).
+    Here the tensor-core tile is picked per expert from its token count, so one granularity serves every type."""
+    if int(quant_type) not in MMQ_TYPES:
+        raise ValueError(f"ggml_moe_get_block_size: ggml quant type {int(quant_type)} has no MMQ kernel")
+    return _MOE_BLOCK
+
+
+def moe_align_block_size(topk_ids: torch.Tensor, block_size: int, num_experts: int):
+    """The token-list layout `ggml_moe_a8` consumes (upstream: vllm `moe_align_block_size`, a separate kernel there; plain
+    torch here -- host-side scheduling, not part of the hot path).  Returns (sorted_token_ids, expert_ids,
+    num_tokens_post_padded): pair indices sorted by expert, every expert's list padded to a multiple of `block_size`
+    with the value `topk_ids.numel()`, and the expert of every block."""
+    flat = topk_ids.reshape(-1).to(torch.int64)
+    numel = flat.numel()
+    counts = torch.bincount(flat, minlength=num_experts)[:num_experts]
+    padded = (counts + block_size - 1) // block_size * block_size
+    ends = torch.cumsum(padded, 0)
+    starts = ends - padded
+    total = numel + num_experts * (block_size - 1)
+    total = (total + block_size - 1) // block_size * block_size
+    sorted_ids = torch.full((total,), numel, dtype=torch.int32, device=flat.device)
+    order = torch.argsort(flat, stable=True)
+    ranks = torch.arange(numel, device=flat.device) - (torch.cumsum(counts, 0) - counts)[flat[order]]
+    sorted_ids[starts[flat[order]] + ranks] = order.to(torch.int32)
+    nblocks = total // block_size
+    expert_ids = torch.searchsorted(ends, torch.arange(nblocks, device=flat.device) * block_size, right=True)
+    expert_ids = expert_ids.clamp_(max=num_experts - 1).to(torch.int32)
+    return sorted_ids, expert_ids, ends[-1:].to(torch.int32)
+
+
+def ggml_moe_a8(X: torch.Tensor, W: torch.Tensor, sorted_token_ids: torch.Tensor, expert_ids: torch.Tensor,
+                num_tokens_post_padded: torch.Tensor, quant_type: int, row: int, top_k: int, tokens: int) -> torch.Tensor:
+    """MoE matmul for prefill: every expert's token list goes through the tensor-core MMQ kernel (`ggml_mul_mat_a8`).
+    X [tokens, K]; W [E, row, bytes]; (sorted_token_ids, expert_ids, num_tokens_post_padded) as produced by
+    `moe_align_block_size(topk_ids, ggml_moe_get_block_size(type), E)`.  Returns [tokens * top_k, row]; pair i = token
+    i // top_k.  Host-scheduled: ONE device->host read of the block -> expert map, then gather + MMQ + scatter per
+    non-empty expert (a grouped tile scheduler inside the MMQ kernel is the next step)."""
+    what = "ggml_moe_a8"
+    _check_x(X, W, what)
+    if X.dim() != 2 or X.shape[0] != tokens:
+        raise ValueError(f"{what}: X must be [tokens, K]")
+    if int(quant_type) not in MMQ_TYPES:
+        raise ValueError(f"{what}: ggml quant type {int(quant_type)} has no MMQ kernel (use ggml_moe_a8_vec)")
+    K = X.shape[1]
+    E = _check_experts(W, quant_type, row, K, what)
+    pairs = int(tokens) * int(top_k)
+    block = _MOE_BLOCK
+    n_pad = int(num_tokens_post_padded.item())              # the one host read
+    if n_pad % block or n_pad > sorted_token_ids.numel():
+        raise ValueError(f"{what}: num_tokens_post_padded = {n_pad} is not a multiple of the block size {block} "
+                         "inside sorted_token_ids")
+    blocks = expert_ids[: n_pad // block].tolist()
+    # one spare row catches the padding entries (id == pairs) of every scatter
+    out = torch.zeros((pairs + 1, int(row)), dtype=X.dtype, device=W.device)
+    slots_all = sorted_token_ids[:n_pad].to(torch.int64).clamp_(max=pairs)
+    tok_all = (slots_all // int(top_k)).clamp_(max=int(tokens) - 1)
+    b0 = 0
+    while b0 < len(blocks):
+        e = blocks[b0]
+        b1 = b0
+        while b1 < len(blocks) and blocks[b1] == e:
+            b1 += 1
+        if not 0 <= e < E:
+            raise ValueError(f"{what}: expert id {e} outside [0, {E})")
+        sl = slice(b0 * block, b1 * block)
+        ye = ggml_mul_mat_a8(W[e], X.index_select(0, tok_all[sl]), quant_type, row)
+        out.index_copy_(0, slots_all[sl], ye)
+        b0 = b1
+    return out[:pairs]
 
 
 def mmvq_fused_supported(quant_type: int, B: int, K: int) -> bool:

@@ -20,7 +20,7 @@ SYMBOLS = (
     "ggb_version", "ggb_last_error", "ggb_set_option", "ggb_block_elems", "ggb_block_bytes",
     "ggb_dequantize", "ggb_q8_1_bytes", "ggb_quantize_q8_1",
     "ggb_mmvq_workspace_bytes", "ggb_mmvq", "ggb_mmvq_gather", "ggb_mmvq_fused", "ggb_mmq_workspace_bytes", "ggb_mmq",
-    "ggb_mmvq_fused_supported", "ggb_debug_mmvq_trace", "ggb_tp_barrier",
+    "ggb_mmvq_fused_supported", "ggb_debug_mmvq_trace", "ggb_tp_barrier", "ggb_moe_mmvq",
 )
 
 
@@ -54,6 +54,7 @@ def _load() -> ctypes.CDLL:
     L.ggb_debug_mmvq_trace.argtypes = [vp]
     L.ggb_debug_mmvq_trace.restype = None
     L.ggb_tp_barrier.argtypes = [ctypes.POINTER(vp), ci, ci, vp]
+    L.ggb_moe_mmvq.argtypes = [vp, vp, vp, vp, ci, ci, i64, i64, i64, i64, i64, vp]
     L.ggb_mmq_workspace_bytes.argtypes = [ci, i64, i64, i64]
     L.ggb_mmq_workspace_bytes.restype = i64
     L.ggb_mmq.argtypes = [vp, vp, vp, ci, ci, i64, i64, i64, i64, vp, i64, vp]

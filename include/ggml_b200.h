@@ -165,6 +165,23 @@ int         ggb_mmvq_fused(const void *W, const void *X, const void *X2, int64_t
 int         ggb_tp_barrier(void *const *flag_peers, int n_peers, int rank, void *stream);
 
 /*
+ * Grouped MMVQ for mixture-of-experts decode.  No counterpart in this reference; the op is
+ * the ggml_moe_a8_vec of the reference's upstream (vLLM csrc/quantization/gguf: quantize_row_q8_1 + moe_vec_q*), whose
+ * argument meaning it keeps:
+ *   W         raw GGUF bytes of n_experts stacked matrices, uint8 [n_experts, N, K/QK*block_bytes], contiguous;
+ *   X         [tokens, K] activations (xy_dtype);      topk_ids  int32 [tokens * top_k], row-major [tokens, top_k];
+ *   Y         [tokens * top_k, N]:  Y[i, :] = q8_1(X[i / top_k, :]) . W[topk_ids[i]]^T   (the caller weights and sums
+ *             the top_k rows of a token).  With top_k = 1 and tokens = the number of pairs this is the second (down)
+ *             projection of an expert MLP: one activation row per pair.
+ * An id outside [0, n_experts) yields a zero output row (the upstream kernel reads out of bounds).  Every ggml_type of
+ * ggb_mmvq, any number of tokens, ONE launch per 65535 pairs (grid = row ranges x pairs, each CTA quantizes its pair's
+ * activation row in shared memory); no workspace.  Numerics: exactly ggb_mmvq's generic kernel at batch 1 -- integer dots
+ * exact, fp32 sums in a (type, K)-dependent order.
+ */
+int         ggb_moe_mmvq(const void *W, const void *X, const int32_t *topk_ids, void *Y, int type, int xy_dtype,
+                         int64_t tokens, int64_t top_k, int64_t n_experts, int64_t K, int64_t N, void *stream);
+
+/*
  * MMQ: Y[M, N] (row stride ldy elements) = q8_1_mmq(X[M, K]) . W[N, K]^T.
  * Replaces ggml_mul_mat_a8 (ggml/mmq.cu:180-255): quantize_mmq_q8_1_cuda + mul_mat_q
  * (ggml/mmq.cuh:1917-2031).  `ws` must hold ggb_mmq_workspace_bytes(...) bytes (the quantized
