@@ -415,11 +415,13 @@ def ggml_moe_a8(X: torch.Tensor, W: torch.Tensor, sorted_token_ids: torch.Tensor
     E = _check_experts(W, quant_type, row, K, what)
     pairs = int(tokens) * int(top_k)
     block = _MOE_BLOCK
-    n_pad = int(num_tokens_post_padded.item())              # the one host read
-    if n_pad % block or n_pad > sorted_token_ids.numel():
+    # the one host read: the padded length and the block -> expert map together
+    head = torch.cat([num_tokens_post_padded.reshape(-1)[:1].to(torch.int64), expert_ids.reshape(-1).to(torch.int64)]).tolist()
+    n_pad = head[0]
+    if n_pad % block or n_pad > sorted_token_ids.numel() or n_pad // block > len(head) - 1:
         raise ValueError(f"{what}: num_tokens_post_padded = {n_pad} is not a multiple of the block size {block} "
-                         "inside sorted_token_ids")
-    blocks = expert_ids[: n_pad // block].tolist()
+                         "inside sorted_token_ids / expert_ids")
+    blocks = head[1:1 + n_pad // block]
     # one spare row catches the padding entries (id == pairs) of every scatter
     out = torch.zeros((pairs + 1, int(row)), dtype=X.dtype, device=W.device)
     slots_all = sorted_token_ids[:n_pad].to(torch.int64).clamp_(max=pairs)
