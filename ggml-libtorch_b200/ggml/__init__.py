@@ -432,11 +432,10 @@ def ggml_moe_a8(X: torch.Tensor, W: torch.Tensor, sorted_token_ids: torch.Tensor
         b1 = b0
         while b1 < len(blocks) and blocks[b1] == e:
             b1 += 1
-        if not 0 <= e < E:
-            raise ValueError(f"{what}: expert id {e} outside [0, {E})")
-        sl = slice(b0 * block, b1 * block)
-        ye = ggml_mul_mat_a8(W[e], X.index_select(0, tok_all[sl]), quant_type, row)
-        out.index_copy_(0, slots_all[sl], ye)
+        if 0 <= e < E:                  # an id outside [0, E) (an expert held by another rank): its rows stay zero, as in the vec op
+            sl = slice(b0 * block, b1 * block)
+            ye = ggml_mul_mat_a8(W[e], X.index_select(0, tok_all[sl]), quant_type, row)
+            out.index_copy_(0, slots_all[sl], ye)
         b0 = b1
     return out[:pairs]
 
